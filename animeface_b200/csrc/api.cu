@@ -1,0 +1,103 @@
+// Library-level entry points and the convolution dispatcher of libsg2b200.
+#include "common.cuh"
+#include "conv.h"
+
+namespace sg2 {
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+// impl: 0 auto, 1 SIMT fp32, 2 tcgen05.  Returns the implementation that will run.
+static int resolve_impl(int impl, bool tc_ok) {
+    if (impl == 1) return 1;
+    if (impl == 2) return tc_ok ? 2 : -1;
+    return tc_ok ? 2 : 1;
+}
+}  // namespace sg2
+
+using namespace sg2;
+
+extern "C" int sg2_version(void) { return 100; }
+extern "C" const char* sg2_last_error(void) { return g_err; }
+extern "C" int64_t sg2_launch_count(void) { return (int64_t)g_launches.load(); }
+
+// The packed buffer always starts with a 16-byte header {impl, transpose, co, ci} so a mismatched
+// pack/conv pair is caught instead of silently computing garbage.
+struct PackHeader { int impl, transpose, co, ci; };
+
+extern "C" int64_t sg2_conv2d_packed_size(int co, int ci, int k, int impl) {
+    if (co <= 0 || ci <= 0 || (k != 1 && k != 3)) return -1;
+    long long simt = (long long)co * ci * k * k * 4;
+    long long tc = conv_packed_bytes_tc(co, ci, k);
+    (void)impl;
+    return 256 + (simt > tc ? simt : tc);
+}
+
+static int pick_impl_for_pack(int co, int ci, int k, int transpose, int impl) {
+    // packing does not know n,h,w: use the channel constraints only (the conv re-checks).
+    const int cin = transpose ? co : ci, cout = transpose ? ci : co;
+    return resolve_impl(impl, conv_tc_supported(1, 16, 16, cin, cout, k));
+}
+
+__global__ void write_header_kernel(PackHeader* h, PackHeader v) { *h = v; }
+
+extern "C" int sg2_conv2d_pack_weight(const float* w, void* packed, int co, int ci, int k,
+                                      float coef, int transpose, int impl, sg2_stream_t stream) {
+    SG2_REQUIRE(w && packed, "conv2d_pack_weight: null pointer");
+    SG2_REQUIRE(co > 0 && ci > 0 && (k == 1 || k == 3), "conv2d_pack_weight: unsupported shape co=%d ci=%d k=%d", co, ci, k);
+    const int use = pick_impl_for_pack(co, ci, k, transpose, impl);
+    if (use < 0) return fail(SG2_ENOTSUP, "conv2d_pack_weight: tcgen05 path does not take co=%d ci=%d k=%d", co, ci, k);
+    cudaStream_t st = (cudaStream_t)stream;
+    PackHeader hv{use, transpose ? 1 : 0, co, ci};
+    write_header_kernel<<<1, 1, 0, st>>>((PackHeader*)packed, hv);
+    int rc = launched("pack_header");
+    if (rc) return rc;
+    void* body = (char*)packed + 256;
+    if (use == 1) return conv_pack_simt(w, (float*)body, co, ci, k, coef, transpose, st);
+    return conv_pack_tc(w, body, co, ci, k, coef, transpose, st);
+}
+
+extern "C" int sg2_conv2d_fwd(const float* x, const void* packed_w, float* y, const int64_t y_strides[4],
+                              int n, int h, int w, int ci, int co, int k,
+                              const float* in_scale, const float* out_scale, const float* bias,
+                              const float* noise, int act, float alpha, float gain,
+                              int impl, sg2_stream_t stream) {
+    SG2_REQUIRE(x && packed_w && y, "conv2d_fwd: null pointer");
+    SG2_REQUIRE(n > 0 && h > 0 && w > 0 && ci > 0 && co > 0, "conv2d_fwd: empty tensor");
+    SG2_REQUIRE(k == 1 || k == 3, "conv2d_fwd: kernel size %d not supported (1 or 3)", k);
+    SG2_REQUIRE(act == 1 || act == 3, "conv2d_fwd: act must be 1 (linear) or 3 (lrelu)");
+    SG2_REQUIRE((long long)n * h * w * (long long)(ci > co ? ci : co) <= (1LL << 40), "conv2d_fwd: tensor is too large");
+    // impl must match what the weight was packed for: the caller passes the same `impl` to both;
+    // channel constraints are identical, spatial constraints are re-checked here.
+    const int packed_for = resolve_impl(impl, conv_tc_supported(1, 16, 16, ci, co, k));
+    if (packed_for < 0) return fail(SG2_ENOTSUP, "conv2d_fwd: tcgen05 path does not take ci=%d co=%d k=%d", ci, co, k);
+    ConvParams p;
+    p.x = x; p.wp = (const char*)packed_w + 256; p.y = y;
+    for (int i = 0; i < 4; ++i) p.ys[i] = y_strides[i];
+    p.n = n; p.h = h; p.w = w; p.ci = ci; p.co = co; p.k = k;
+    p.in_scale = in_scale; p.out_scale = out_scale; p.bias = bias; p.noise = noise;
+    p.act = act; p.alpha = alpha; p.gain = gain;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (packed_for == 2) {
+        if (!conv_tc_supported(n, h, w, ci, co, k))
+            return fail(SG2_ENOTSUP, "conv2d_fwd: tcgen05 path does not take n=%d h=%d w=%d (pack with impl=1)", n, h, w);
+        return conv_fwd_tc(p, st);
+    }
+    return conv_fwd_simt(p, st);
+}
+
+extern "C" int sg2_conv2d_wgrad(const float* x, const float* gy, float* dw,
+                                int n, int h, int w, int ci, int co, int k, float coef,
+                                const float* in_scale, const float* out_scale,
+                                int accumulate, int impl, sg2_stream_t stream) {
+    SG2_REQUIRE(x && gy && dw, "conv2d_wgrad: null pointer");
+    SG2_REQUIRE(n > 0 && h > 0 && w > 0 && ci > 0 && co > 0, "conv2d_wgrad: empty tensor");
+    SG2_REQUIRE(k == 1 || k == 3, "conv2d_wgrad: kernel size %d not supported (1 or 3)", k);
+    WgradParams p;
+    p.x = x; p.gy = gy; p.dw = dw; p.n = n; p.h = h; p.w = w; p.ci = ci; p.co = co; p.k = k;
+    p.coef = coef; p.in_scale = in_scale; p.out_scale = out_scale; p.chunk = 0;
+    const int use = resolve_impl(impl, wgrad_tc_supported(n, h, w, ci, co, k));
+    if (use < 0) return fail(SG2_ENOTSUP, "conv2d_wgrad: tcgen05 path does not take this shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (use == 2) return conv_wgrad_tc(p, accumulate, st);
+    return conv_wgrad_simt(p, accumulate, st);
+}

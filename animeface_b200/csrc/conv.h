@@ -1,0 +1,45 @@
+// Internal parameter blocks shared by the convolution kernels (SIMT and tcgen05) and the C-ABI shim.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sg2 {
+
+struct ConvParams {
+    const float* x;        // [n,h,w,ci] NHWC dense
+    const void* wp;        // packed weight (layout depends on impl)
+    float* y;              // output, strides ys (n,c,h,w) in elements
+    long long ys[4];
+    int n, h, w, ci, co, k;
+    const float* in_scale;   // [n,ci] or null
+    const float* out_scale;  // [n,co] or null
+    const float* bias;       // [co] or null
+    const float* noise;      // [n,h,w] or null
+    int act;                 // 1 linear, 3 lrelu
+    float alpha, gain;
+};
+
+struct WgradParams {
+    const float* x;        // [n,h,w,ci]
+    const float* gy;       // [n,h,w,co]
+    float* dw;             // [co,ci,k,k]
+    int n, h, w, ci, co, k;
+    float coef;
+    const float* in_scale;   // [n,ci] or null
+    const float* out_scale;  // [n,co] or null
+    long long chunk;         // pixels per split (set by the launcher)
+};
+
+int conv_fwd_simt(const ConvParams& p, cudaStream_t st);
+int conv_wgrad_simt(WgradParams p, int accumulate, cudaStream_t st);
+int conv_pack_simt(const float* w, float* wp, int co, int ci, int k, float coef, int transpose, cudaStream_t st);
+
+// tcgen05 path (conv_tc.cu)
+bool conv_tc_supported(int n, int h, int w, int ci, int co, int k);
+bool wgrad_tc_supported(int n, int h, int w, int ci, int co, int k);
+int conv_fwd_tc(const ConvParams& p, cudaStream_t st);
+int conv_wgrad_tc(WgradParams p, int accumulate, cudaStream_t st);
+int conv_pack_tc(const float* w, void* wp, int co, int ci, int k, float coef, int transpose, cudaStream_t st);
+long long conv_packed_bytes_tc(int co, int ci, int k);
+
+}  // namespace sg2

@@ -1,0 +1,173 @@
+// upfirdn2d for sm_100a: pad -> zero-insert upsample -> FIR -> decimate in one launch.
+// Semantics follow thirdparty/stylegan3_ops/ops/upfirdn2d.py:161-207 (_upfirdn2d_ref) and the
+// plugin entry thirdparty/stylegan3_ops/ops/upfirdn2d.cpp:10; the kernels are new.
+//
+//   y[n,c,jy,jx] = gain * sum_{ty,tx} U[jy*downy + ty - pady0, jx*downx + tx - padx0] * wt[ty][tx]
+//   U[ky,kx]     = x[ky/upy, kx/upx] when ky%upy==0, kx%upx==0 and inside the image, else 0
+//   wt[ty][tx]   = flip ? f[ty][tx] : f[fh-1-ty][fw-1-tx]
+//
+// HBM-bound (algorithmic bytes = |x| + |y|).  Two kernels:
+//   * upfirdn2d_vec4_nhwc : fp32 channels_last, C % 4 == 0 -- one thread = one output pixel x 4
+//     channels, 128-bit coalesced loads/stores, taps served from L1, only non-zero phases visited.
+//   * upfirdn2d_generic<T>: any dtype / strides / factors, thread order follows y's memory order.
+#include "common.cuh"
+
+namespace sg2 {
+
+struct UpfirdnParams {
+    const void* x; const float* f; void* y;
+    int n, c, in_h, in_w, out_h, out_w;
+    long long xs[4], ys[4];          // element strides (n,c,h,w)
+    int fh, fw, upx, upy, downx, downy, padx0, pady0, flip;
+    float gain;
+    int order[4];                    // dims of y sorted by decreasing stride (memory order)
+    long long total;
+};
+
+__device__ __forceinline__ int pos_mod(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
+
+template <class T> struct Acc { typedef float type; };
+template <> struct Acc<double> { typedef double type; };
+
+template <class T>
+__global__ void __launch_bounds__(256) upfirdn2d_generic(UpfirdnParams p) {
+    typedef typename Acc<T>::type acc_t;
+    const T* __restrict__ x = (const T*)p.x;
+    T* __restrict__ y = (T*)p.y;
+    const int size[4] = {p.n, p.c, p.out_h, p.out_w};
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < p.total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int coord[4];
+        long long r = idx;
+#pragma unroll
+        for (int k = 3; k >= 0; --k) { int d = p.order[k]; coord[d] = (int)(r % size[d]); r /= size[d]; }
+        const int in_ = coord[0], ic = coord[1], jy = coord[2], jx = coord[3];
+        const int basey = jy * p.downy - p.pady0, basex = jx * p.downx - p.padx0;
+        const int ty0 = pos_mod(-basey, p.upy), tx0 = pos_mod(-basex, p.upx);
+        const T* xp = x + in_ * p.xs[0] + ic * p.xs[1];
+        acc_t acc = 0;
+        for (int ty = ty0; ty < p.fh; ty += p.upy) {
+            int ky = basey + ty;
+            if (ky < 0) continue;
+            int iy = ky / p.upy;
+            if (iy >= p.in_h) break;
+            int fy = p.flip ? ty : p.fh - 1 - ty;
+            for (int tx = tx0; tx < p.fw; tx += p.upx) {
+                int kx = basex + tx;
+                if (kx < 0) continue;
+                int ix = kx / p.upx;
+                if (ix >= p.in_w) break;
+                int fx = p.flip ? tx : p.fw - 1 - tx;
+                acc += (acc_t)xp[iy * p.xs[2] + ix * p.xs[3]] * (acc_t)p.f[fy * p.fw + fx];
+            }
+        }
+        y[in_ * p.ys[0] + ic * p.ys[1] + jy * p.ys[2] + jx * p.ys[3]] = (T)(acc * (acc_t)p.gain);
+    }
+}
+
+// fp32 channels_last fast path.  Grid: x = pixel tiles of one image row strip, threads cover
+// (pixels-in-tile x channel quads) with the channel quad fastest => 128-bit coalesced.
+constexpr int kMaxTaps = 32 * 32;
+
+__global__ void __launch_bounds__(256) upfirdn2d_vec4_nhwc(UpfirdnParams p) {
+    __shared__ float sf[kMaxTaps];
+    for (int i = threadIdx.x; i < p.fh * p.fw; i += blockDim.x) {
+        int ty = i / p.fw, tx = i % p.fw;          // stored already oriented: sf[ty][tx] = wt * gain
+        int fy = p.flip ? ty : p.fh - 1 - ty, fx = p.flip ? tx : p.fw - 1 - tx;
+        sf[i] = p.f[fy * p.fw + fx] * p.gain;
+    }
+    __syncthreads();
+    const float* __restrict__ x = (const float*)p.x;
+    float* __restrict__ y = (float*)p.y;
+    const int cq = p.c >> 2;
+    const long long total = (long long)p.n * p.out_h * p.out_w * cq;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int q = (int)(idx % cq);
+        long long pix = idx / cq;
+        int jx = (int)(pix % p.out_w); pix /= p.out_w;
+        int jy = (int)(pix % p.out_h);
+        int in_ = (int)(pix / p.out_h);
+        const int basey = jy * p.downy - p.pady0, basex = jx * p.downx - p.padx0;
+        const int ty0 = pos_mod(-basey, p.upy), tx0 = pos_mod(-basex, p.upx);
+        const float* xp = x + in_ * p.xs[0] + 4 * q;
+        float4 acc = f4zero();
+        for (int ty = ty0; ty < p.fh; ty += p.upy) {
+            int ky = basey + ty;
+            if (ky < 0) continue;
+            int iy = ky / p.upy;
+            if (iy >= p.in_h) break;
+            const float* xr = xp + iy * p.xs[2];
+            const float* fr = sf + ty * p.fw;
+#pragma unroll 4
+            for (int tx = tx0; tx < p.fw; tx += p.upx) {
+                int kx = basex + tx;
+                if (kx < 0) continue;
+                int ix = kx / p.upx;
+                if (ix >= p.in_w) break;
+                fma4(acc, fr[tx], ldg4(xr + ix * p.xs[3]));
+            }
+        }
+        st4_cs(y + in_ * p.ys[0] + jy * p.ys[2] + jx * p.ys[3] + 4 * q, acc);
+    }
+}
+
+}  // namespace sg2
+
+using namespace sg2;
+
+extern "C" int sg2_upfirdn2d(const void* x, const float* f, void* y, int dtype,
+                             int n, int c, int in_h, int in_w, const int64_t x_strides[4],
+                             int out_h, int out_w, const int64_t y_strides[4],
+                             int fh, int fw, int upx, int upy, int downx, int downy,
+                             int padx0, int padx1, int pady0, int pady1,
+                             int flip, float gain, sg2_stream_t stream) {
+    // argument checks mirror thirdparty/stylegan3_ops/ops/upfirdn2d.cpp:13-34
+    SG2_REQUIRE(x && f && y, "upfirdn2d: null pointer");
+    SG2_REQUIRE(n > 0 && c > 0 && in_h > 0 && in_w > 0, "upfirdn2d: x has zero size");
+    SG2_REQUIRE(fh >= 1 && fw >= 1, "upfirdn2d: f must be at least 1x1");
+    SG2_REQUIRE(upx >= 1 && upy >= 1, "upfirdn2d: upsampling factor must be at least 1");
+    SG2_REQUIRE(downx >= 1 && downy >= 1, "upfirdn2d: downsampling factor must be at least 1");
+    SG2_REQUIRE(dtype == SG2_F32 || dtype == SG2_F16 || dtype == SG2_F64, "upfirdn2d: unsupported dtype %d", dtype);
+    const int ow = (in_w * upx + padx0 + padx1 - fw + downx) / downx;
+    const int oh = (in_h * upy + pady0 + pady1 - fh + downy) / downy;
+    SG2_REQUIRE(ow >= 1 && oh >= 1, "upfirdn2d: output must be at least 1x1");
+    SG2_REQUIRE(ow == out_w && oh == out_h, "upfirdn2d: output size mismatch (expected %dx%d, got %dx%d)", oh, ow, out_h, out_w);
+    const long long total = (long long)n * c * out_h * out_w;
+    SG2_REQUIRE(total <= 2147483647LL && (long long)n * c * in_h * in_w <= 2147483647LL, "upfirdn2d: tensor is too large");
+
+    UpfirdnParams p;
+    p.x = x; p.f = f; p.y = y;
+    p.n = n; p.c = c; p.in_h = in_h; p.in_w = in_w; p.out_h = out_h; p.out_w = out_w;
+    for (int i = 0; i < 4; ++i) { p.xs[i] = x_strides[i]; p.ys[i] = y_strides[i]; }
+    p.fh = fh; p.fw = fw; p.upx = upx; p.upy = upy; p.downx = downx; p.downy = downy;
+    p.padx0 = padx0; p.pady0 = pady0; p.flip = flip ? 1 : 0; p.gain = gain; p.total = total;
+    // memory order of y: sort dims by decreasing stride (size-1 dims go first, they do not matter)
+    int ord[4] = {0, 1, 2, 3};
+    const int size[4] = {n, c, out_h, out_w};
+    for (int i = 0; i < 4; ++i)
+        for (int j = i + 1; j < 4; ++j) {
+            long long si = size[ord[i]] == 1 ? (1LL << 62) : p.ys[ord[i]];
+            long long sj = size[ord[j]] == 1 ? (1LL << 62) : p.ys[ord[j]];
+            if (sj > si) { int t = ord[i]; ord[i] = ord[j]; ord[j] = t; }
+        }
+    for (int i = 0; i < 4; ++i) p.order[i] = ord[i];
+
+    cudaStream_t st = (cudaStream_t)stream;
+    const int threads = 256;
+    const bool nhwc_dense = p.xs[1] == 1 && p.ys[1] == 1 && (c % 4) == 0 &&
+                            p.xs[3] == c && p.ys[3] == c && p.xs[2] == (long long)in_w * c &&
+                            p.ys[2] == (long long)out_w * c && (p.xs[0] % 4) == 0 && (p.ys[0] % 4) == 0 &&
+                            ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0;
+    if (dtype == SG2_F32 && nhwc_dense && fh * fw <= kMaxTaps) {
+        long long work = total / 4;
+        int blocks = (int)std::min<long long>(ceil_div(work, threads), (long long)num_sms() * 32);
+        upfirdn2d_vec4_nhwc<<<blocks, threads, 0, st>>>(p);
+        return launched("upfirdn2d_vec4_nhwc");
+    }
+    int blocks = (int)std::min<long long>(ceil_div(total, threads), (long long)num_sms() * 32);
+    if (dtype == SG2_F32)      upfirdn2d_generic<float><<<blocks, threads, 0, st>>>(p);
+    else if (dtype == SG2_F16) upfirdn2d_generic<__half><<<blocks, threads, 0, st>>>(p);
+    else                       upfirdn2d_generic<double><<<blocks, threads, 0, st>>>(p);
+    return launched("upfirdn2d_generic");
+}

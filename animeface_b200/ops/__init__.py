@@ -1,0 +1,2 @@
+"""Operators of the StyleGAN2 hot path, each a thin autograd wrapper over one libsg2b200 entry point."""
+from . import bias_act, conv2d, mbstd, resample, upfirdn2d  # noqa: F401

@@ -1,0 +1,282 @@
+"""Dense and modulated 2-D convolution on libsg2b200 (stride 1, 'same' zero padding, k in {1, 3}).
+
+Replaces, for the StyleGAN2 path of the reference:
+  * ``nn.Conv2d`` inside ``ELR``                    implementations/StyleGAN2/model.py:29-37, 50-53
+  * ``ModulatedConv2d.forward``                      implementations/StyleGAN2/model.py:106-132
+  * their autograd (``convolution_backward``), composed as a closed family of three ops --
+    forward conv, data-gradient conv, weight-gradient -- exactly the way
+    thirdparty/stylegan3_ops/ops/conv2d_gradfix.py:99-187 composes them, so gradients of arbitrary
+    order exist (R1 needs the second order: nnutils/loss/penalty.py:11-26, 85-101).
+
+Layout: activations are logical NCHW tensors in ``torch.channels_last`` memory format (NHWC in HBM);
+weights keep the reference layout ``[co, ci, k, k]`` and are packed per call by the library.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import _lib
+
+IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
+_default_impl = IMPL_AUTO
+
+
+def set_default_impl(impl: int) -> None:
+    """0 = auto (tcgen05 where supported, else fp32 SIMT), 1 = force SIMT, 2 = force tcgen05."""
+    global _default_impl
+    assert impl in (0, 1, 2)
+    _default_impl = impl
+
+
+def _cl(x: torch.Tensor) -> torch.Tensor:
+    """Dense channels_last view of a 4-D tensor (copy only if needed)."""
+    n, c, h, w = x.shape
+    want = (h * w * c, 1, w * c, c)
+    if x.stride() == want:
+        return x
+    # torch treats size-1 dims as "any stride": normalise explicitly.
+    y = torch.empty_strided((n, c, h, w), want, dtype=x.dtype, device=x.device)
+    y.copy_(x)
+    return y
+
+
+def _empty_cl(n, c, h, w, like: torch.Tensor) -> torch.Tensor:
+    return torch.empty_strided((n, c, h, w), (h * w * c, 1, w * c, c), dtype=torch.float32, device=like.device)
+
+
+def _pack(w: torch.Tensor, coef: float, transpose: bool, impl: int) -> torch.Tensor:
+    lib = _lib.load()
+    co, ci, k, _ = w.shape
+    nbytes = lib.sg2_conv2d_packed_size(co, ci, k, impl)
+    if nbytes < 0:
+        raise RuntimeError(f'conv2d: unsupported weight shape {tuple(w.shape)}')
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    wc = w.detach().contiguous()
+    _lib.check(lib.sg2_conv2d_pack_weight(wc.data_ptr(), buf.data_ptr(), co, ci, k, float(coef),
+                                          1 if transpose else 0, impl, _lib.stream_ptr(w)), 'sg2_conv2d_pack_weight')
+    return buf
+
+
+def _conv_raw(x, w, coef, transpose, in_scale=None, out_scale=None, bias=None, noise=None,
+              slope=None, out_nchw=False, impl=None):
+    """One library call: y = act(out_scale * conv(x * in_scale, w*coef) + bias + noise).
+
+    transpose=True runs the data-gradient conv (x has w.shape[0] channels, y has w.shape[1])."""
+    impl = _default_impl if impl is None else impl
+    _lib.require_cuda(x, w)
+    lib = _lib.load()
+    co, ci, k, _ = w.shape
+    cin, cout = (co, ci) if transpose else (ci, co)
+    n, cx, h, wd = x.shape
+    if cx != cin:
+        raise RuntimeError(f'conv2d: input has {cx} channels, weight expects {cin}')
+    if x.dtype != torch.float32 or w.dtype != torch.float32:
+        raise RuntimeError('conv2d: float32 only')
+    x = _cl(x)
+    packed = _pack(w, coef, transpose, impl)
+    if out_nchw:
+        y = torch.empty((n, cout, h, wd), dtype=torch.float32, device=x.device)
+    else:
+        y = _empty_cl(n, cout, h, wd, x)
+    f32 = lambda t: None if t is None else t.detach().to(torch.float32).contiguous()
+    in_scale, out_scale, bias, noise = f32(in_scale), f32(out_scale), f32(bias), f32(noise)
+    _lib.check(lib.sg2_conv2d_fwd(
+        x.data_ptr(), packed.data_ptr(), y.data_ptr(), _lib.strides4(y), n, h, wd, cin, cout, k,
+        _lib.ptr(in_scale), _lib.ptr(out_scale), _lib.ptr(bias), _lib.ptr(noise),
+        3 if slope is not None else 1, float(slope if slope is not None else 0.0), 1.0,
+        impl, _lib.stream_ptr(x)), 'sg2_conv2d_fwd')
+    return y
+
+
+def _wgrad_raw(x, gy, k, coef, in_scale=None, out_scale=None, impl=None):
+    impl = _default_impl if impl is None else impl
+    _lib.require_cuda(x, gy)
+    lib = _lib.load()
+    n, ci, h, wd = x.shape
+    co = gy.shape[1]
+    x, gy = _cl(x), _cl(gy)
+    dw = torch.empty((co, ci, k, k), dtype=torch.float32, device=x.device)
+    f32 = lambda t: None if t is None else t.detach().to(torch.float32).contiguous()
+    in_scale, out_scale = f32(in_scale), f32(out_scale)
+    _lib.check(lib.sg2_conv2d_wgrad(x.data_ptr(), gy.data_ptr(), dw.data_ptr(), n, h, wd, ci, co, k, float(coef),
+                                    _lib.ptr(in_scale), _lib.ptr(out_scale), 0, impl, _lib.stream_ptr(x)),
+               'sg2_conv2d_wgrad')
+    return dw
+
+
+# ----------------------------------------------------------------------------------------------
+# The closed family (any-order autograd).  `coef` is the ELR constant folded into the weight.
+
+class Conv2dFn(torch.autograd.Function):
+    """y = conv2d(x, w * coef), stride 1, same padding."""
+
+    @staticmethod
+    def forward(ctx, x, w, coef):
+        ctx.coef = coef
+        ctx.save_for_backward(x, w)
+        return _conv_raw(x, w, coef, False)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = Conv2dTransposeFn.apply(gy, w, ctx.coef)
+        if ctx.needs_input_grad[1]:
+            gw = Conv2dWgradFn.apply(x, gy, w.shape[2], ctx.coef)
+        return gx, gw, None
+
+
+class Conv2dTransposeFn(torch.autograd.Function):
+    """gx = conv_transpose2d(gy, w * coef) (the data gradient of Conv2dFn)."""
+
+    @staticmethod
+    def forward(ctx, gy, w, coef):
+        ctx.coef = coef
+        ctx.save_for_backward(gy, w)
+        return _conv_raw(gy, w, coef, True)
+
+    @staticmethod
+    def backward(ctx, g):
+        gy, w = ctx.saved_tensors
+        ggy = gw = None
+        if ctx.needs_input_grad[0]:
+            ggy = Conv2dFn.apply(g, w, ctx.coef)
+        if ctx.needs_input_grad[1]:
+            gw = Conv2dWgradFn.apply(g, gy, w.shape[2], ctx.coef)
+        return ggy, gw, None
+
+
+class Conv2dWgradFn(torch.autograd.Function):
+    """dw[co,ci,k,k] = coef * sum_{n,h,w} gy (x) x (the weight gradient of Conv2dFn)."""
+
+    @staticmethod
+    def forward(ctx, x, gy, k, coef):
+        ctx.coef = coef
+        ctx.save_for_backward(x, gy)
+        return _wgrad_raw(x, gy, k, coef)
+
+    @staticmethod
+    def backward(ctx, gdw):
+        x, gy = ctx.saved_tensors
+        gx = ggy = None
+        if ctx.needs_input_grad[0]:
+            gx = Conv2dTransposeFn.apply(gy, gdw, ctx.coef)
+        if ctx.needs_input_grad[1]:
+            ggy = Conv2dFn.apply(x, gdw, ctx.coef)
+        return gx, ggy, None, None
+
+
+def conv2d(x, w, coef: float = 1.0):
+    """Drop-in for ``conv2d_gradfix.conv2d(x, w*coef, padding=k//2)`` (stride 1, odd k)."""
+    return Conv2dFn.apply(x, w, float(coef))
+
+
+# ----------------------------------------------------------------------------------------------
+# Fused conv + bias + leaky-ReLU (discriminator layers).  Forward is ONE kernel; the backward is
+# built from the closed family + the bias_act gradient op, so it stays twice differentiable.
+
+class ConvBiasActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, coef, slope):
+        y = _conv_raw(x, w, coef, False, bias=b, slope=slope)
+        ctx.coef, ctx.slope = coef, slope
+        ctx.save_for_backward(x, w, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        from .bias_act import act_grad
+        x, w, y = ctx.saved_tensors
+        gu = act_grad(gy, y, ctx.slope) if ctx.slope is not None else gy
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = Conv2dTransposeFn.apply(gu, w, ctx.coef)
+        if ctx.needs_input_grad[1]:
+            gw = Conv2dWgradFn.apply(x, gu, w.shape[2], ctx.coef)
+        if ctx.needs_input_grad[2]:
+            gb = gu.sum((0, 2, 3))
+        return gx, gw, gb, None, None
+
+
+def conv2d_bias_act(x, w, b, coef: float = 1.0, slope: float | None = 0.2):
+    """lrelu_slope(conv2d(x * coef, w) + b): Conv2d('elr') + LeakyReLU (model.py:50-53, 191-193).
+    slope=None -> no activation (the DBlock skip conv, model.py:201)."""
+    return ConvBiasActFn.apply(x, w, b, float(coef), slope)
+
+
+# ----------------------------------------------------------------------------------------------
+# Modulated convolution (generator).  First-order autograd; the per-sample weight tensor
+# [B, Co, Ci, k, k] of the reference (model.py:115-120) is never materialised.
+
+class ModConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, s, d, b, noise, coef, slope, out_nchw):
+        y = _conv_raw(x, w, coef, False, in_scale=s, out_scale=d, bias=b, noise=noise, slope=slope, out_nchw=out_nchw)
+        ctx.coef, ctx.slope, ctx.out_nchw = coef, slope, out_nchw
+        ctx.save_for_backward(x, w, s, d if d is not None else torch.empty(0, device=x.device),
+                              b if b is not None else torch.empty(0, device=x.device),
+                              noise if noise is not None else torch.empty(0, device=x.device), y)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        lib = _lib.load()
+        x, w, s, d, b, noise, y = ctx.saved_tensors
+        d = d if d.numel() else None
+        b = b if b.numel() else None
+        noise = noise if noise.numel() else None
+        n, ci, h, wd = x.shape
+        co, k = w.shape[0], w.shape[2]
+        st = _lib.stream_ptr(x)
+        x = _cl(x)
+        if co % 4 == 0:
+            gy, yc = _cl(gy), _cl(y)
+            g_acc = _empty_cl(n, co, h, wd, x)
+            gb_part = torch.empty((n, co), dtype=torch.float32, device=x.device)
+            gd = torch.empty((n, co), dtype=torch.float32, device=x.device) if d is not None else None
+            bflat = None if b is None else b.detach().reshape(-1).contiguous()
+            _lib.check(lib.sg2_modconv_bwd_prep(
+                gy.data_ptr(), yc.data_ptr(), _lib.ptr(noise), _lib.ptr(bflat), _lib.ptr(d), g_acc.data_ptr(),
+                gb_part.data_ptr(), _lib.ptr(gd), n, h * wd, co,
+                float(ctx.slope if ctx.slope is not None else 1.0), st), 'sg2_modconv_bwd_prep')
+            gb = gb_part.sum(0)
+        else:
+            # few output channels (ToRGB, Co=3): the tensors are tiny, keep this prologue in torch.
+            assert ctx.slope is None and d is None
+            g_acc = gy
+            gb = gy.sum((0, 2, 3))
+            gd = None
+        gx = gw = gs = None
+        # data gradient w.r.t. the modulated input, then gs = sum_hw g_xs * x and gx = g_xs * s in one pass
+        g_xs = _conv_raw(g_acc, w, ctx.coef, True)
+        if ci % 4 == 0:
+            gs = torch.empty((n, ci), dtype=torch.float32, device=x.device)
+            gx = _empty_cl(n, ci, h, wd, x) if ctx.needs_input_grad[0] else None
+            sc = s.detach().contiguous()
+            _lib.check(lib.sg2_scale_reduce_hw(g_xs.data_ptr(), x.data_ptr(), sc.data_ptr(), _lib.ptr(gx),
+                                               gs.data_ptr(), n, h * wd, ci, st), 'sg2_scale_reduce_hw')
+        else:
+            gs = (g_xs * x).sum((2, 3))
+            gx = g_xs * s[:, :, None, None]
+        if ctx.needs_input_grad[1]:
+            gw = _wgrad_raw(x, g_acc, k, ctx.coef, in_scale=s)
+        if b is not None:
+            gb = gb.reshape(b.shape)
+        return gx, gw, gs, gd, (gb if b is not None else None), None, None, None, None
+
+
+def modulated_conv2d(x, w, s, bias=None, noise=None, demod=True, slope=None, eps=1e-4, out_nchw=False):
+    """ModulatedConv2d.forward (model.py:106-132) (+ InjectNoise :85-88 + LeakyReLU :164 when given).
+
+    x [B,Ci,H,W]; w [Co,Ci,k,k]; s [B,Ci] = affine(style) + 1 (model.py:110); bias [1,Co,1,1];
+    noise [B,1,H,W].  The demodulation coefficient d[b,o] = rsqrt(sum_i s^2 * sum_k (w*coef)^2 + eps)
+    is a tiny [B,Ci]x[Ci,Co] product kept in torch so its gradients reach `s` and `w` through autograd."""
+    co, ci, k, _ = w.shape
+    coef = 1.0 / float(ci * k * k) ** 0.5
+    d = None
+    if demod:
+        wsq = w.square().sum((2, 3))                       # [Co,Ci]
+        d = torch.rsqrt(torch.matmul(s.square(), wsq.t()) * (coef * coef) + eps)
+    return ModConvFn.apply(x, w, s, d, bias, noise, coef, slope, out_nchw)

@@ -1,0 +1,190 @@
+/*
+ * sg2b200.h -- C ABI of libsg2b200.so: the B200 (sm_100a) kernels behind the
+ * StyleGAN2 G+D training step of STomoya/animeface.
+ *
+ * Every entry point is what the reference's pybind11 plugin layer (or the ATen
+ * call it makes) for this path would bind.  The reference interface each entry
+ * replaces is cited as  <file>:<line>  relative to the reference checkout.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless
+ *     stated otherwise; no torch types.
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on
+ *     that stream and never synchronises.
+ *   - return value 0 = success, negative = error (SG2_E*); the message for the
+ *     calling thread is available through sg2_last_error().
+ *   - strides are in ELEMENTS, order (n, c, h, w), so NCHW-contiguous and
+ *     channels_last (NHWC) tensors are both described without copies -- the
+ *     same contract as upfirdn2d.cpp:32 / bias_act.cpp:41 (output keeps the
+ *     input's memory format).
+ *   - dtype codes: SG2_F32 = 0, SG2_F16 = 1, SG2_F64 = 2 (internal math is fp32,
+ *     fp64 for SG2_F64 -- thirdparty/stylegan3_ops/ops/upfirdn2d.cu:9-12).
+ */
+#ifndef SG2B200_H
+#define SG2B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SG2_OK        0
+#define SG2_EINVAL   -1   /* bad argument (what TORCH_CHECK raises in the reference) */
+#define SG2_ELAUNCH  -2   /* CUDA launch / runtime error */
+#define SG2_ENOTSUP  -3   /* valid request, no kernel for it */
+
+#define SG2_F32 0
+#define SG2_F16 1
+#define SG2_F64 2
+
+typedef void* sg2_stream_t;
+
+/* library ------------------------------------------------------------------ */
+int         sg2_version(void);
+const char* sg2_last_error(void);
+/* number of kernels this library has launched in the calling process. */
+int64_t     sg2_launch_count(void);
+
+/* upfirdn2d ---------------------------------------------------------------- *
+ * replaces: thirdparty/stylegan3_ops/ops/upfirdn2d.cpp:10  (pybind `upfirdn2d`)
+ *           + kernels thirdparty/stylegan3_ops/ops/upfirdn2d.cu:23,92
+ * Pad -> zero-insert upsample -> FIR -> decimate, one launch.
+ * f: [fh, fw] float32, contiguous.  out_h/out_w must equal
+ *   (in*up + pad0 + pad1 - f + down) / down      (upfirdn2d.cpp:29-30).      */
+int sg2_upfirdn2d(const void* x, const float* f, void* y, int dtype,
+                  int n, int c, int in_h, int in_w, const int64_t x_strides[4],
+                  int out_h, int out_w, const int64_t y_strides[4],
+                  int fh, int fw, int upx, int upy, int downx, int downy,
+                  int padx0, int padx1, int pady0, int pady1,
+                  int flip, float gain, sg2_stream_t stream);
+
+/* StyleGAN2 resampling (channels_last fp32) ---------------------------------- *
+ * replaces: implementations/StyleGAN2/model.py:56-58 (Upsample2x 'bilinear',
+ *           align_corners=False) followed by model.py:138-149 (Blur2d,
+ *           [1,2,1]x[1,2,1]/16, zero pad 1) -- ONE pass, replicate-then-zero
+ *           border.  blur=0 gives the bare bilinear x2 of ToImage
+ *           (model.py:243,248-249).
+ * layout: x [n,h,w,c] / y [n,2h,2w,c] dense NHWC when nhwc=1, else dense NCHW.
+ * scale: optional [n,c] per-(sample,channel) factor applied to the output.
+ * The *_adj entry is the exact adjoint (backward of fwd; and fwd is the
+ * backward of adj, so the pair is closed under differentiation).             */
+int sg2_up2x_fwd(const float* x, float* y, const float* scale,
+                 int n, int c, int h, int w, int nhwc, int blur, sg2_stream_t stream);
+int sg2_up2x_adj(const float* gy, float* gx, const float* scale,
+                 int n, int c, int h, int w, int nhwc, int blur, sg2_stream_t stream);
+
+/* replaces: implementations/StyleGAN2/model.py:61-63 (AvgPool2d(2)) and the
+ * residual merge (x + t)/sqrt(2) of DBlock.forward model.py:209-212.
+ * y = alpha * (avg2x2(x) + (t ? avg2x2(t) : 0)).   x,t [n,h,w,c] NHWC dense, h,w even.
+ * adj: gx = alpha * 0.25 * gy broadcast over each 2x2 window.                 */
+int sg2_avgpool2_fwd(const float* x, const float* t, float* y, float alpha,
+                     int n, int c, int h, int w, sg2_stream_t stream);
+int sg2_avgpool2_adj(const float* gy, float* gx, float alpha,
+                     int n, int c, int h, int w, sg2_stream_t stream);
+
+/* bias_act ----------------------------------------------------------------- *
+ * replaces: thirdparty/stylegan3_ops/ops/bias_act.cpp:26 (pybind `bias_act`)
+ *           + kernel thirdparty/stylegan3_ops/ops/bias_act.cu:17-141
+ * Works on the flat dense buffer: b index = (i / step_b) % size_b
+ * (bias_act.cpp:47-48), so contiguous and channels_last need no copy.
+ * Null pointer = "absent" (the reference's empty tensor, bias_act.py:31).
+ * grad: 0 forward, 1 first-order, 2 second-order.  act: 1 linear 2 relu
+ * 3 lrelu 4 tanh 5 sigmoid 6 elu 7 selu 8 softplus 9 swish (bias_act.py:16-26).
+ * clamp < 0 disables clamping.                                               */
+int sg2_bias_act(const void* x, const void* b, const void* xref, const void* yref,
+                 const void* dy, void* y, int dtype, int64_t numel,
+                 int size_b, int64_t step_b, int grad, int act,
+                 float alpha, float gain, float clamp, sg2_stream_t stream);
+
+/* minibatch stddev --------------------------------------------------------- *
+ * replaces: implementations/StyleGAN2/model.py:215-236 (MiniBatchStdDev.forward;
+ *           = nnutils/module/layers.py:40-52).
+ * x [n,c,h,w] (strides given) -> y [n,c+1,h,w] (strides given): y[:, :c] = x,
+ * y[:, c] = mean_{c,h,w} sqrt(var_g(x) + eps) of the sample's group column.
+ * `groups` = G as resolved by the caller (group_size if n % group_size == 0
+ * else n, model.py:234-236); sample i belongs to column m = i % (n/G).
+ * stat: [n/G] float32 workspace/output (the per-column statistic).
+ * bwd: gx = gy[:, :c] + d(stat)/dx * sum_{g,h,w} gy[g*M+m, c, h, w].          */
+int sg2_mbstd_fwd(const float* x, const int64_t x_strides[4], float* y,
+                  const int64_t y_strides[4], float* stat,
+                  int n, int c, int h, int w, int groups, float eps, sg2_stream_t stream);
+int sg2_mbstd_bwd(const float* x, const int64_t x_strides[4], const float* gy,
+                  const int64_t gy_strides[4], float* gx, const int64_t gx_strides[4],
+                  int n, int c, int h, int w, int groups, float eps, sg2_stream_t stream);
+
+/* dense / modulated convolution ------------------------------------------- *
+ * replaces: the ATen/cuDNN calls of the path --
+ *   F.conv2d(groups=B) of ModulatedConv2d.forward implementations/StyleGAN2/model.py:106-132,
+ *   nn.Conv2d inside ELR model.py:29-37,50-53 (DBlock model.py:186-212),
+ *   and their autograd (convolution_backward: dgrad + wgrad), composed exactly as
+ *   thirdparty/stylegan3_ops/ops/conv2d_gradfix.py:99-187 composes them.
+ * Stride-1 "same" cross-correlation, odd square kernel k (1 or 3), zero padding.
+ * x  [n,h,w,ci] NHWC dense fp32;  y [n,h,w,co] with explicit strides (n,c,h,w).
+ *
+ * Weights are passed PACKED: sg2_conv2d_pack_weight turns the reference layout
+ * w[co][ci][k][k] into the operand layout of the selected kernel, folding the
+ * ELR coefficient (`coef`, model.py:32,105) in.  transpose=1 packs the weight of
+ * the data-gradient conv (ci<->co swapped, taps flipped): dgrad is then the SAME
+ * forward kernel applied to gy.
+ *
+ * Fused prologue/epilogue of sg2_conv2d_fwd (any pointer may be NULL):
+ *   in_scale  [n,ci]   style modulation s[b,i] applied to x      (model.py:115)
+ *   out_scale [n,co]   demodulation d[b,o]                         (model.py:118-120)
+ *   bias      [co]                                                  (model.py:132)
+ *   noise     [n,h,w]  InjectNoise, added unscaled                  (model.py:85-88)
+ *   act: 1 linear, 3 lrelu(alpha); then * gain                      (model.py:164)
+ *   y = gain * act( out_scale * conv(x * in_scale, w) + bias + noise )
+ * impl: 0 = auto, 1 = fp32 SIMT kernel, 2 = tcgen05 (bf16x3 split) kernel.    */
+int64_t sg2_conv2d_packed_size(int co, int ci, int k, int impl);   /* bytes */
+int sg2_conv2d_pack_weight(const float* w, void* packed, int co, int ci, int k,
+                           float coef, int transpose, int impl, sg2_stream_t stream);
+int sg2_conv2d_fwd(const float* x, const void* packed_w, float* y, const int64_t y_strides[4],
+                   int n, int h, int w, int ci, int co, int k,
+                   const float* in_scale, const float* out_scale, const float* bias,
+                   const float* noise, int act, float alpha, float gain,
+                   int impl, sg2_stream_t stream);
+/* weight gradient: dw[co][ci][k][k] (reference layout) = coef * sum_{n,h,w} gy (x) x.
+ * x [n,h,w,ci], gy [n,h,w,co] NHWC dense.  in_scale [n,ci] / out_scale [n,co]
+ * optional: x is taken as x*in_scale and gy as gy*out_scale (modulated layers).
+ * accumulate=0 overwrites dw, 1 adds into it.                                 */
+int sg2_conv2d_wgrad(const float* x, const float* gy, float* dw,
+                     int n, int h, int w, int ci, int co, int k, float coef,
+                     const float* in_scale, const float* out_scale,
+                     int accumulate, int impl, sg2_stream_t stream);
+
+/* per-(sample,channel) reductions used by the modulated-conv backward ------- *
+ * replaces: the autograd graph of ModulatedConv2d.forward
+ *           (implementations/StyleGAN2/model.py:106-132).
+ * a, bm, a_out: [n,hw,c] NHWC dense, c % 4 == 0.
+ *   out[b,c]   = sum_hw a * (bm ? bm : 1)         (d s[b,i] = sum_hw x * g_xs)
+ *   a_out      = a * scale[b,c]   when a_out != NULL  (g_x = g_xs * s, same pass)  */
+int sg2_reduce_hw(const float* a, const float* bm, float* out,
+                  int n, int hw, int c, sg2_stream_t stream);
+int sg2_scale_reduce_hw(const float* a, const float* bm, const float* scale,
+                        float* a_out, float* out, int n, int hw, int c, sg2_stream_t stream);
+/* backward prologue of y = lrelu_alpha(d * acc + bias + noise) in ONE pass over (gy, y):
+ *   gu = gy * (y > 0 ? 1 : alpha);  g_acc = gu * d;  gb_part[b,o] = sum_hw gu;
+ *   gd[b,o] = sum_hw gu * acc,  acc recovered from y as (u - bias - noise)/d.
+ * alpha = 1 means "no activation".  d, gd, bias, noise may be NULL.           */
+int sg2_modconv_bwd_prep(const float* gy, const float* y, const float* noise, const float* bias,
+                         const float* d, float* g_acc, float* gb_part, float* gd,
+                         int n, int hw, int c, float alpha, sg2_stream_t stream);
+
+/* optimizer ---------------------------------------------------------------- *
+ * replaces: torch.optim.Adam.step (implementations/StyleGAN2/utils.py:220-221,
+ *           85-86,112-113; ~125 per-tensor launches) over ONE flat fp32 buffer,
+ *           and update_ema (nnutils/training.py:23-40; 81 lerps) likewise.
+ * p,g,m,v [numel]; ema may be NULL (else ema = decay*ema + (1-decay)*p_new).
+ * grad_scale multiplies g first (1/world after the all-reduce).
+ * step: 1-based step count of this segment, held on the DEVICE (int64) so the
+ * call replays inside a CUDA graph; the caller increments it.                 */
+int sg2_adam_ema(float* p, const float* g, float* m, float* v, float* ema,
+                 int64_t numel, const int64_t* step, float lr, float beta1, float beta2,
+                 float eps, float grad_scale, float ema_decay, sg2_stream_t stream);
+int sg2_ema_update(float* ema, const float* p, int64_t numel, float decay, sg2_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SG2B200_H */
