@@ -21,6 +21,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import rng
 from .ops import conv2d as C
 from .ops.mbstd import minibatch_stddev
 from .ops.resample import avgpool2, upsample2x_bilinear, upsample2x_blur
@@ -96,23 +97,8 @@ class MapLinear(nn.Module):
         return self.linear(x) * self.lr
 
 
-_noise_queue: list | None = None
-
-
-class supplied_noise:
-    """Context manager for tests: InjectNoise pops tensors from ``seq`` instead of calling torch.randn."""
-
-    def __init__(self, seq):
-        self.seq = list(seq)
-
-    def __enter__(self):
-        global _noise_queue
-        _noise_queue = self.seq
-        return self
-
-    def __exit__(self, *exc):
-        global _noise_queue
-        _noise_queue = None
+class supplied_noise(rng.replay):
+    """Context manager for tests: InjectNoise takes its tensors from ``seq`` instead of torch.randn."""
 
 
 class InjectNoise(nn.Module):
@@ -123,9 +109,7 @@ class InjectNoise(nn.Module):
         self.scale = nn.Parameter(torch.zeros(1))
 
     def sample(self, B, H, W, device):
-        if _noise_queue is not None:
-            return _noise_queue.pop(0).to(device)
-        return torch.randn(B, 1, H, W, device=device)
+        return rng.randn(B, 1, H, W, device=device)
 
     def forward(self, x):
         B, _, H, W = x.size()

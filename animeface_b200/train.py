@@ -1,0 +1,151 @@
+"""The StyleGAN2 G+D training step of the reference on the B200 kernels.
+
+Reference: the loop body of implementations/StyleGAN2/utils.py:53-116 (``train``) and the optimizer set-up
+:208-221.  Same losses, same lazy-R1 schedule (the GAN loss is DROPPED on R1 steps, :71-76), same Adam
+hyper-parameters, same random-draw order.  What is removed from the timed step are the reference's host
+round trips: ``save_image`` every step (:124), ``.item()`` / ``isnan().any()`` syncs (:127-130); losses stay on
+the device.  Two equivalences are used (results identical, work skipped):
+  * D phase: G runs under no_grad (the reference builds the graph and detaches, :67-69);
+  * G phase: D's parameters do not require grad (the reference computes their gradients and then discards them
+    at the next ``zero_grad``, :55-56).
+Path-length regularisation (:18-33, 96-103) is off by default in the reference (pl_lambda = 0, :159) and not
+built yet.
+"""
+from __future__ import annotations
+
+import functools
+from dataclasses import dataclass
+
+import torch
+
+from . import rng
+from .diffaugment import DiffAugment
+from .model import Discriminator, Generator, init_weight_N01, supplied_noise  # noqa: F401
+from .nnutils import FlatAdam, update_ema
+from .nnutils.loss import NonSaturatingLoss, r1_regularizer
+
+
+@dataclass
+class TrainConfig:
+    """Defaults of implementations/StyleGAN2/utils.py:142-160 + utils/argument.py:10-31 at 256 px."""
+    image_size: int = 256
+    image_channels: int = 3
+    style_dim: int = 512
+    channels: int = 32
+    max_channels: int = 512
+    block_num_conv: int = 2
+    map_num_layers: int = 8
+    map_lr: float = 0.01
+    mbsd_groups: int = 4
+    batch_size: int = 32
+    lr: float = 1e-3
+    beta1: float = 0.
+    beta2: float = 0.99
+    g_k: int = 8
+    d_k: int = 16
+    r1_lambda: float = 10.
+    pl_lambda: float = 0.
+    policy: str = 'color,translation'
+    ema_decay: float = 0.999
+
+
+def build_models(cfg: TrainConfig, device):
+    """Models + init exactly as utils.py:186-205."""
+    mk_g = lambda: Generator(cfg.image_size, cfg.image_channels, cfg.style_dim, cfg.channels, cfg.max_channels,
+                             cfg.block_num_conv, cfg.map_num_layers, True, cfg.map_lr)
+    G, G_ema = mk_g(), mk_g()
+    D = Discriminator(cfg.image_size, cfg.image_channels, cfg.channels, cfg.max_channels, cfg.block_num_conv, cfg.mbsd_groups)
+    G.init_weight(map_init_func=functools.partial(init_weight_N01, lr=cfg.map_lr), syn_init_func=init_weight_N01)
+    G_ema.eval()
+    G_ema.load_state_dict(G.state_dict())       # == update_ema(G, G_ema, decay=0) on finite memory (utils.py:199-200)
+    D.apply(init_weight_N01)
+    return G.to(device), G_ema.to(device), D.to(device)
+
+
+def build_optimizers(cfg: TrainConfig, G, G_ema, D):
+    """Lazy-regularisation-scaled Adam (utils.py:208-221) as two FlatAdam instances."""
+    betas = (cfg.beta1, cfg.beta2)
+    if cfg.pl_lambda > 0:
+        r = cfg.g_k / (cfg.g_k + 1)
+        g_lr, g_betas = cfg.lr * r, (betas[0] ** r, betas[1] ** r)
+    else:
+        g_lr, g_betas = cfg.lr, betas
+    if cfg.r1_lambda > 0:
+        r = cfg.d_k / (cfg.d_k + 1)
+        d_lr, d_betas = cfg.lr * r, (betas[0] ** r, betas[1] ** r)
+    else:
+        d_lr, d_betas = cfg.lr, betas
+    opt_g = FlatAdam(G.parameters(), lr=g_lr, betas=g_betas, model=G, ema_model=G_ema)
+    opt_d = FlatAdam(D.parameters(), lr=d_lr, betas=d_betas, model=D)
+    return opt_g, opt_d
+
+
+class Trainer:
+    """One object = the state of the reference's ``train()`` loop; ``step(real)`` = one iteration."""
+
+    def __init__(self, cfg: TrainConfig, G, G_ema, D, opt_g, opt_d):
+        if cfg.pl_lambda > 0:
+            raise NotImplementedError('path-length regularisation is not built yet (off by default in the reference)')
+        self.cfg, self.G, self.G_ema, self.D, self.opt_g, self.opt_d = cfg, G, G_ema, D, opt_g, opt_d
+        self.loss = NonSaturatingLoss()
+        self.r1 = r1_regularizer()
+        self.augment = functools.partial(DiffAugment, policy=cfg.policy)
+        self.batches_done = 0
+        self._d_params = list(D.parameters())
+
+    def is_r1_step(self, it=None):
+        it = self.batches_done if it is None else it
+        return it % self.cfg.d_k == 0 and self.cfg.r1_lambda > 0 and it != 0
+
+    def step(self, real: torch.Tensor):
+        """real: [B,3,H,W] on the device.  Returns (D_loss, G_loss, fake) device tensors; no host sync."""
+        cfg, G, D = self.cfg, self.G, self.D
+        B, dev = real.size(0), real.device
+        self.opt_g.zero_grad()
+        self.opt_d.zero_grad()
+        # ---- discriminator phase (utils.py:60-86)
+        z = rng.randn(B, cfg.style_dim, device=dev)
+        r1_step = self.is_r1_step()
+        real_aug = self.augment(real)
+        with torch.no_grad():
+            fake, _ = G(z)
+            fake_aug = self.augment(fake)
+        if r1_step:
+            # lazy R1 (utils.py:71-76): the GAN loss is dropped, so D(real_aug) / D(fake_aug) of :65,:69 are dead
+            # values -- only their random draws (consumed above) matter for the stream.
+            D_loss = self.r1(real, D, None) * cfg.r1_lambda * cfg.d_k
+        else:
+            D_loss = self.loss.d_loss(D(real_aug), D(fake_aug))
+        D_loss.backward()
+        self.opt_d.step()
+        # ---- generator phase (utils.py:88-113)
+        z = rng.randn(B, cfg.style_dim, device=dev)
+        for p in self._d_params:
+            p.requires_grad_(False)
+        try:
+            fake, _ = G(z)
+            fake_prob = D(self.augment(fake))
+            G_loss = self.loss.g_loss(fake_prob)
+            G_loss.backward()
+        finally:
+            for p in self._d_params:
+                p.requires_grad_(True)
+        self.opt_g.step()
+        update_ema(G, self.G_ema, cfg.ema_decay)
+        self.batches_done += 1
+        return D_loss.detach(), G_loss.detach(), fake.detach()
+
+
+def train(max_iter, dataset, cfg: TrainConfig, device, log_every=100, log=print):
+    """Minimal counterpart of the reference ``train()`` (utils.py:35-138): iterate a loader of real batches."""
+    G, G_ema, D = build_models(cfg, device)
+    opt_g, opt_d = build_optimizers(cfg, G, G_ema, D)
+    trainer = Trainer(cfg, G, G_ema, D, opt_g, opt_d)
+    while trainer.batches_done < max_iter:
+        for real in dataset:
+            d_loss, g_loss, _ = trainer.step(real.to(device, non_blocking=True))
+            if log_every and trainer.batches_done % log_every == 0:
+                log(f'{trainer.batches_done}/{max_iter} D={d_loss.item():.4f} G={g_loss.item():.4f}')
+            if trainer.batches_done >= max_iter:
+                break
+    return trainer
