@@ -71,6 +71,8 @@ def _dense(x: torch.Tensor) -> torch.Tensor:
 
 def _like(t: torch.Tensor, ref: torch.Tensor) -> torch.Tensor:
     """t laid out with ref's strides -- the kernel walks flat buffers (bias_act.cpp:10-22)."""
+    if ref is None:
+        return _dense(t)
     if t.stride() == ref.stride():
         return t
     out = torch.empty_strided(ref.shape, ref.stride(), dtype=t.dtype, device=t.device)

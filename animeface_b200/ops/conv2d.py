@@ -20,6 +20,26 @@ from .. import _lib
 IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
 _default_impl = IMPL_AUTO
 
+# bench.py sets this to a list to time every convolution launch with CUDA events on the launching stream:
+# entries are (kind, flops, start_event, end_event).  None = no timing (the default).
+launch_log = None
+
+
+class _timed:
+    def __init__(self, kind, flops):
+        self.kind, self.flops = kind, flops
+
+    def __enter__(self):
+        if launch_log is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if launch_log is not None:
+            self.e1.record()
+            launch_log.append((self.kind, self.flops, self.e0, self.e1))
+
 
 def set_default_impl(impl: int) -> None:
     """0 = auto (tcgen05 where supported, else fp32 SIMT), 1 = force SIMT, 2 = force tcgen05."""
@@ -80,11 +100,12 @@ def _conv_raw(x, w, coef, transpose, in_scale=None, out_scale=None, bias=None, n
         y = _empty_cl(n, cout, h, wd, x)
     f32 = lambda t: None if t is None else t.detach().to(torch.float32).contiguous()
     in_scale, out_scale, bias, noise = f32(in_scale), f32(out_scale), f32(bias), f32(noise)
-    _lib.check(lib.sg2_conv2d_fwd(
-        x.data_ptr(), packed.data_ptr(), y.data_ptr(), _lib.strides4(y), n, h, wd, cin, cout, k,
-        _lib.ptr(in_scale), _lib.ptr(out_scale), _lib.ptr(bias), _lib.ptr(noise),
-        3 if slope is not None else 1, float(slope if slope is not None else 0.0), 1.0,
-        impl, _lib.stream_ptr(x)), 'sg2_conv2d_fwd')
+    with _timed('dgrad' if transpose else 'fwd', 2.0 * n * h * wd * cin * cout * k * k):
+        _lib.check(lib.sg2_conv2d_fwd(
+            x.data_ptr(), packed.data_ptr(), y.data_ptr(), _lib.strides4(y), n, h, wd, cin, cout, k,
+            _lib.ptr(in_scale), _lib.ptr(out_scale), _lib.ptr(bias), _lib.ptr(noise),
+            3 if slope is not None else 1, float(slope if slope is not None else 0.0), 1.0,
+            impl, _lib.stream_ptr(x)), 'sg2_conv2d_fwd')
     return y
 
 
@@ -98,9 +119,10 @@ def _wgrad_raw(x, gy, k, coef, in_scale=None, out_scale=None, impl=None):
     dw = torch.empty((co, ci, k, k), dtype=torch.float32, device=x.device)
     f32 = lambda t: None if t is None else t.detach().to(torch.float32).contiguous()
     in_scale, out_scale = f32(in_scale), f32(out_scale)
-    _lib.check(lib.sg2_conv2d_wgrad(x.data_ptr(), gy.data_ptr(), dw.data_ptr(), n, h, wd, ci, co, k, float(coef),
-                                    _lib.ptr(in_scale), _lib.ptr(out_scale), 0, impl, _lib.stream_ptr(x)),
-               'sg2_conv2d_wgrad')
+    with _timed('wgrad', 2.0 * n * h * wd * ci * co * k * k):
+        _lib.check(lib.sg2_conv2d_wgrad(x.data_ptr(), gy.data_ptr(), dw.data_ptr(), n, h, wd, ci, co, k, float(coef),
+                                        _lib.ptr(in_scale), _lib.ptr(out_scale), 0, impl, _lib.stream_ptr(x)),
+                   'sg2_conv2d_wgrad')
     return dw
 
 

@@ -1,0 +1,260 @@
+"""bench.py -- StyleGAN2 256x256 G+D training step, images/sec (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's B200 path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port), rank 0 only
+
+Workload = BASELINE config 2 ("StyleGAN2 256x256, batch 32, 1xB200, R1 every 16 steps"): defaults of
+implementations/StyleGAN2/utils.py:142-160 at image_size 256, fp32 (AMP off -- the parity configuration),
+DiffAugment 'color,translation', lazy R1 (d_k = 16), synthetic uniform[-1,1] images, reference init.
+A step = Trainer.step = D phase + G phase + EMA (the loop body of utils.py:53-116).
+One JSON line on stdout (rank 0).  N > 1: launched by torchrun, one rank per GPU, B = 32 per GPU (weak scaling),
+one NCCL all-reduce of the flat gradient buffer per optimizer step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_IMG_STEP = 370.7e9          # D phase 217.7 + G phase 152.9 GFLOP per image, normal step
+
+
+def load_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        return dict(hbm=float(p['hbm_gbs']), tf=float(p['bf16_tflops_sustained']), src='measured')
+    except Exception:
+        return dict(hbm=6650.0, tf=1400.0, src='fallback')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (recipe's clocks line)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=(max(mx) if mx else None),
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------------
+def cpu_oracle_step_rate(batch, steps, warmup, threads=None):
+    """img/s of the reference's CPU path (oracle port, plain PyTorch fp32) on this host's cores."""
+    import torch
+    from oracle import sg2_torch as T
+    if threads:
+        torch.set_num_threads(threads)
+    gen = torch.Generator().manual_seed(0)
+    sd_g = {k: v.requires_grad_(not k.endswith('.kernel')) for k, v in T.init_generator_sd(gen=gen).items()}
+    sd_d = {k: v.requires_grad_(True) for k, v in T.init_discriminator_sd(gen=gen).items()}
+    sd_e = {k: v.detach().clone() for k, v in sd_g.items()}
+    cfg = T.StepConfig()
+    g_lr, g_b, d_lr, d_b = T.adam_hparams(cfg)
+    opt_g = torch.optim.Adam([v for v in sd_g.values() if v.requires_grad], lr=g_lr, betas=g_b)
+    opt_d = torch.optim.Adam(list(sd_d.values()), lr=d_lr, betas=d_b)
+    rng = T.FreshDraws('cpu')
+    times = []
+    for it in range(warmup + steps):
+        real = torch.rand(batch, 3, 256, 256) * 2 - 1
+        t0 = time.perf_counter()
+        T.train_step(sd_g, sd_d, sd_e, opt_g, opt_d, real, it + 1, rng, cfg)     # it+1: never index 0; R1 when (it+1)%16==0
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return batch * steps / total, total / steps, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    batch = 4 if args.steps + args.warmup <= 30 else 2
+    ips, sec, cores = cpu_oracle_step_rate(batch, args.steps, args.warmup)
+    sample = f'oracle port (oracle/sg2_torch.py, plain PyTorch fp32 CPU) of the same step at B={batch} per step, {args.steps} timed steps'
+    line = dict(impl='reference', metric='StyleGAN2 256px G+D step images/sec', value=round(ips, 4), unit='images/sec',
+                n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=round(sec * 1e3, 1),
+                higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+                config=dict(workload='StyleGAN2 256x256 config of implementations/StyleGAN2 (channels=32, style_dim=512), '
+                                     'R1 every 16 steps, DiffAugment color,translation; CPU sample', batch_per_step=batch),
+                cpu_baseline=dict(value=round(ips, 4), unit='images/sec', cores=cores, kind='port', sample=sample),
+                e2e=dict(value=round(ips, 4), unit='images/sec', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from animeface_b200 import _lib
+    from animeface_b200.nnutils import init_distributed
+    from animeface_b200.ops import conv2d as C
+    from animeface_b200.train import TrainConfig, Trainer, build_models, build_optimizers
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device and there is no CPU fallback for the product path')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        init_distributed('nccl')
+    peaks = load_peaks()
+    B = args.batch
+    cfg = TrainConfig(batch_size=B)
+    torch.manual_seed(0)                                 # identical replicas (weights), rank-distinct data below
+    G, G_ema, D = build_models(cfg, dev)
+    opt_g, opt_d = build_optimizers(cfg, G, G_ema, D)
+    tr = Trainer(cfg, G, G_ema, D, opt_g, opt_d)
+    torch.manual_seed(1000 + rank)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # resident synthetic batches (uniform [-1,1] like T.Normalize(0.5,0.5) output), a few so steps differ
+    pool = [torch.rand(B, 3, 256, 256, device=dev) * 2 - 1 for _ in range(4)]
+    for i in range(args.warmup):
+        tr.step(pool[i % len(pool)])
+    sync()
+
+    # ---- device-resident timed region: EXACTLY K steps
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    C.launch_log = []
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    e0.record()
+    for i in range(args.steps):
+        tr.step(pool[i % len(pool)])
+    e1.record()
+    sync()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0
+    conv_log, C.launch_log = C.launch_log, None
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    value = world * B * args.steps / (ms / 1e3)
+
+    # roofline of the dominant kernel family: the convolution launches (fwd/dgrad/wgrad implicit GEMMs)
+    conv_ms = sum(a.elapsed_time(b) for _, _, a, b in conv_log)
+    conv_flops = sum(f for _, f, _, _ in conv_log)
+    achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+    by_kind = {}
+    for kind, f, a, b in conv_log:
+        d = by_kind.setdefault(kind, [0.0, 0.0, 0])
+        d[0] += f; d[1] += a.elapsed_time(b); d[2] += 1
+    roofline = dict(bound='tensor', achieved=round(achieved, 2), peak=peaks['tf'], unit='TFLOP/s',
+                    frac=round(achieved / peaks['tf'], 4), traffic=None,
+                    kernel='conv2d fwd/dgrad/wgrad (all launches of the timed region)',
+                    peak_source=f"bf16_tflops_sustained of MEASURED_PEAKS.json ({peaks['src']})",
+                    share_of_step=round(conv_ms / (ms if world == 1 else max(ms, 1e-9)), 3),
+                    launches=len(conv_log),
+                    by_kind={k: dict(tflops=round(v[0] / (v[1] / 1e3) / 1e12, 2), ms=round(v[1], 2), launches=v[2])
+                             for k, v in by_kind.items()})
+
+    # ---- end-to-end: host batch in pinned memory -> H2D each step, losses read back each step
+    host = [torch.empty(B, 3, 256, 256, pin_memory=True).uniform_(-1, 1) for _ in range(2)]
+    sync()
+    e0.record()
+    for i in range(args.steps):
+        real = host[i % 2].to(dev, non_blocking=True)
+        d_loss, g_loss, _ = tr.step(real)
+        _ = (d_loss.item(), g_loss.item())                # D2H read of the step's result
+    e1.record()
+    sync()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t)
+    e2e = dict(value=round(world * B * args.steps / (e2e_ms / 1e3), 2), unit='images/sec',
+               h2d_bytes_per_step=B * 3 * 256 * 256 * 4, d2h_bytes_per_step=8)
+
+    if rank != 0:
+        return
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        ips, sec, cores = cpu_oracle_step_rate(4, 2, 1)
+        cpu_baseline = dict(value=round(ips, 4), unit='images/sec', cores=cores, kind='port',
+                            sample='oracle/sg2_torch.py (plain-PyTorch CPU restatement of the reference step) at B=4: '
+                                   f'1 warm-up + 2 timed steps, {sec:.1f} s/step')
+    line = dict(metric='StyleGAN2 256px G+D step images/sec', value=round(value, 2), unit='images/sec', n_gpus=world,
+                steps=args.steps, warmup=args.warmup, ms_per_step=round(ms / args.steps, 3), higher_is_better=True,
+                scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+                config=dict(workload='BASELINE config 2: StyleGAN2 256x256 (channels=32, max 512, style_dim 512), batch 32 per GPU, '
+                                     'R1 every 16 steps, DiffAugment color,translation, Adam, EMA; fp32 storage',
+                            batch_per_gpu=B, parallelism=f'dp{world}', conv_impl=args.conv_impl,
+                            l2='per-step working set (activations, several GB) >> 126 MB L2; no explicit flush',
+                            r1_steps_in_timed_region=sum(1 for i in range(args.steps) if (args.warmup + i) % cfg.d_k == 0 and (args.warmup + i) != 0),
+                            model_tflops=round(value * FLOP_PER_IMG_STEP / 1e12, 2)),
+                clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu_baseline)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=16)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=32, help='per-GPU batch (BASELINE config 2/3: 32)')
+    ap.add_argument('--conv-impl', default='auto', choices=['auto', 'simt', 'tc'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+        return
+    from animeface_b200.ops import conv2d as C
+    C.set_default_impl(dict(auto=0, simt=1, tc=2)[args.conv_impl])
+    run_b200(args)
+
+
+if __name__ == '__main__':
+    main()
