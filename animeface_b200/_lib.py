@@ -36,6 +36,7 @@ SIGNATURES = {
     'sg2_bias_act': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _i64, _int, _i64, _int, _int, _f, _f, _f, _vp]),
     'sg2_mbstd_fwd': (_int, [_vp, _i64p, _vp, _i64p, _vp, _int, _int, _int, _int, _int, _f, _vp]),
     'sg2_mbstd_bwd': (_int, [_vp, _i64p, _vp, _i64p, _vp, _i64p, _int, _int, _int, _int, _int, _f, _vp]),
+    'sg2_conv2d_select_impl': (_int, [_int, _int, _int, _int, _int, _int, _int, _int]),
     'sg2_conv2d_packed_size': (_i64, [_int, _int, _int, _int]),
     'sg2_conv2d_pack_weight': (_int, [_vp, _vp, _int, _int, _int, _f, _int, _int, _vp]),
     'sg2_conv2d_fwd': (_int, [_vp, _vp, _vp, _i64p, _int, _int, _int, _int, _int, _int,

@@ -6,11 +6,13 @@ namespace sg2 {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 
-// impl: 0 auto, 1 SIMT fp32, 2 tcgen05.  Returns the implementation that will run.
-static int resolve_impl(int impl, bool tc_ok) {
+// impl codes: 0 auto, 1 fp32 SIMT, 2 tcgen05 bf16x3, 3 tcgen05 tf32x3 + promotion (fp32-class; forward convs).
+// Returns the implementation that will run, or -1 when an explicitly requested one does not take the shape.
+static int resolve_impl(int impl, int precise, int n, int h, int w, int ci, int co, int k) {
+    const bool tc_ok = conv_tc_supported(n, h, w, ci, co, k);
     if (impl == 1) return 1;
-    if (impl == 2) return tc_ok ? 2 : -1;
-    return tc_ok ? 2 : 1;
+    if (impl == 2 || impl == 3) return tc_ok ? impl : -1;
+    return tc_ok ? (precise ? 3 : 2) : 1;
 }
 }  // namespace sg2
 
@@ -24,18 +26,26 @@ extern "C" int64_t sg2_launch_count(void) { return (int64_t)g_launches.load(); }
 // pack/conv pair is caught instead of silently computing garbage.
 struct PackHeader { int impl, transpose, co, ci; };
 
+extern "C" int sg2_conv2d_select_impl(int n, int h, int w, int ci, int co, int k, int impl, int precise) {
+    if (n <= 0 || h <= 0 || w <= 0 || ci <= 0 || co <= 0 || (k != 1 && k != 3) || impl < 0 || impl > 3) return SG2_EINVAL;
+    const int r = resolve_impl(impl, precise, n, h, w, ci, co, k);
+    return r < 0 ? SG2_ENOTSUP : r;
+}
+
 extern "C" int64_t sg2_conv2d_packed_size(int co, int ci, int k, int impl) {
     if (co <= 0 || ci <= 0 || (k != 1 && k != 3)) return -1;
     long long simt = (long long)co * ci * k * k * 4;
-    long long tc = conv_packed_bytes_tc(co, ci, k);
+    long long tcb = conv_packed_bytes_tc(co, ci, k);
+    long long tc32 = conv_packed_bytes_tc32(co, ci, k);
     (void)impl;
-    return 256 + (simt > tc ? simt : tc);
+    long long m = simt > tcb ? simt : tcb;
+    return 256 + (m > tc32 ? m : tc32);
 }
 
 static int pick_impl_for_pack(int co, int ci, int k, int transpose, int impl) {
-    // packing does not know n,h,w: use the channel constraints only (the conv re-checks).
+    // packing does not know n,h,w: channel constraints only (16x16 stands in for "any supported image size").
     const int cin = transpose ? co : ci, cout = transpose ? ci : co;
-    return resolve_impl(impl, conv_tc_supported(1, 16, 16, cin, cout, k));
+    return resolve_impl(impl, transpose ? 0 : 1, 1, 16, 16, cin, cout, k);
 }
 
 __global__ void write_header_kernel(PackHeader* h, PackHeader v) { *h = v; }
@@ -53,6 +63,7 @@ extern "C" int sg2_conv2d_pack_weight(const float* w, void* packed, int co, int 
     if (rc) return rc;
     void* body = (char*)packed + 256;
     if (use == 1) return conv_pack_simt(w, (float*)body, co, ci, k, coef, transpose, st);
+    if (use == 3) return conv_pack_tc32(w, body, co, ci, k, coef, transpose, st);
     return conv_pack_tc(w, body, co, ci, k, coef, transpose, st);
 }
 
@@ -66,10 +77,12 @@ extern "C" int sg2_conv2d_fwd(const float* x, const void* packed_w, float* y, co
     SG2_REQUIRE(k == 1 || k == 3, "conv2d_fwd: kernel size %d not supported (1 or 3)", k);
     SG2_REQUIRE(act == 1 || act == 3, "conv2d_fwd: act must be 1 (linear) or 3 (lrelu)");
     SG2_REQUIRE((long long)n * h * w * (long long)(ci > co ? ci : co) <= (1LL << 40), "conv2d_fwd: tensor is too large");
-    // impl must match what the weight was packed for: the caller passes the same `impl` to both;
-    // channel constraints are identical, spatial constraints are re-checked here.
-    const int packed_for = resolve_impl(impl, conv_tc_supported(1, 16, 16, ci, co, k));
-    if (packed_for < 0) return fail(SG2_ENOTSUP, "conv2d_fwd: tcgen05 path does not take ci=%d co=%d k=%d", ci, co, k);
+    // The weight must have been packed for the implementation that runs here: callers resolve once with
+    // sg2_conv2d_select_impl and pass the same explicit code to both.  impl = 0 resolves as "precise forward".
+    const int packed_for = resolve_impl(impl, 1, n, h, w, ci, co, k);
+    if (packed_for < 0) return fail(SG2_ENOTSUP, "conv2d_fwd: tcgen05 path does not take n=%d h=%d w=%d ci=%d co=%d k=%d", n, h, w, ci, co, k);
+    if (impl == 0 && packed_for == 1 && conv_tc_supported(1, 16, 16, ci, co, k))
+        return fail(SG2_ENOTSUP, "conv2d_fwd: image size %dx%d needs the SIMT kernel; pack and call with impl=1", h, w);
     ConvParams p;
     p.x = x; p.wp = (const char*)packed_w + 256; p.y = y;
     for (int i = 0; i < 4; ++i) p.ys[i] = y_strides[i];
@@ -77,11 +90,8 @@ extern "C" int sg2_conv2d_fwd(const float* x, const void* packed_w, float* y, co
     p.in_scale = in_scale; p.out_scale = out_scale; p.bias = bias; p.noise = noise;
     p.act = act; p.alpha = alpha; p.gain = gain;
     cudaStream_t st = (cudaStream_t)stream;
-    if (packed_for == 2) {
-        if (!conv_tc_supported(n, h, w, ci, co, k))
-            return fail(SG2_ENOTSUP, "conv2d_fwd: tcgen05 path does not take n=%d h=%d w=%d (pack with impl=1)", n, h, w);
-        return conv_fwd_tc(p, st);
-    }
+    if (packed_for == 2) return conv_fwd_tc(p, st);
+    if (packed_for == 3) return conv_fwd_tc32(p, st);
     return conv_fwd_simt(p, st);
 }
 
@@ -95,9 +105,10 @@ extern "C" int sg2_conv2d_wgrad(const float* x, const float* gy, float* dw,
     WgradParams p;
     p.x = x; p.gy = gy; p.dw = dw; p.n = n; p.h = h; p.w = w; p.ci = ci; p.co = co; p.k = k;
     p.coef = coef; p.in_scale = in_scale; p.out_scale = out_scale; p.chunk = 0;
-    const int use = resolve_impl(impl, wgrad_tc_supported(n, h, w, ci, co, k));
-    if (use < 0) return fail(SG2_ENOTSUP, "conv2d_wgrad: tcgen05 path does not take this shape");
+    const bool wtc = wgrad_tc_supported(n, h, w, ci, co, k);
+    if (impl >= 2 && !wtc) return fail(SG2_ENOTSUP, "conv2d_wgrad: tcgen05 path does not take this shape");
+    const int use = impl == 1 ? 1 : (wtc ? 2 : 1);
     cudaStream_t st = (cudaStream_t)stream;
-    if (use == 2) return conv_wgrad_tc(p, accumulate, st);
+    if (use >= 2) return conv_wgrad_tc(p, accumulate, st);
     return conv_wgrad_simt(p, accumulate, st);
 }

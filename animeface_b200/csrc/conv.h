@@ -42,4 +42,9 @@ int conv_wgrad_tc(WgradParams p, int accumulate, cudaStream_t st);
 int conv_pack_tc(const float* w, void* wp, int co, int ci, int k, float coef, int transpose, cudaStream_t st);
 long long conv_packed_bytes_tc(int co, int ci, int k);
 
+// tcgen05 path, fp32-class precision (conv_tc32.cu): forward convolutions
+int conv_fwd_tc32(const ConvParams& p, cudaStream_t st);
+int conv_pack_tc32(const float* w, void* wp, int co, int ci, int k, float coef, int transpose, cudaStream_t st);
+long long conv_packed_bytes_tc32(int co, int ci, int k);
+
 }  // namespace sg2

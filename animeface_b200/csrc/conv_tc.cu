@@ -19,9 +19,7 @@
 //              one cp.async.bulk per K step.
 //   Epilogue : tcgen05.ld -> out_scale (demod) / bias / noise / leaky-ReLU / gain -> global (NHWC, 128-bit stores).
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = transform, then epilogue.
-#include <cuda.h>
-#include <cuda_bf16.h>
-#include "common.cuh"
+#include "tc_common.cuh"
 #include "conv.h"
 
 namespace sg2 {
@@ -39,78 +37,6 @@ constexpr int STAGE_A = 2 * BM * KSTEP * 2;      // 32 KB: A_hi + A_lo
 __host__ __device__ constexpr int stage_b(int bn) { return 2 * bn * KSTEP * 2; }   // B_hi + B_lo
 __host__ __device__ constexpr int smem_bytes(int bn) { return 1024 + STAGES * (STAGE_F32 + STAGE_A + stage_b(bn)) + 256; }
 
-// ---- PTX wrappers -------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void mma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 B, 8-row atoms of 1024 B, dense):
-// start>>4 | LBO(=1, ignored for swizzled K-major)<<16 | SBO(1024>>4)<<32 | version 1<<46 | layout SWIZZLE_128B(2)<<61
-__device__ __forceinline__ uint64_t kmajor_desc(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
-           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-// instruction descriptor: D=f32 (bit4), A=B=bf16 (bits 7,10), both K-major, N>>3 at bit 17, M>>4 at bit 24
-__host__ __device__ constexpr uint32_t idesc_bf16(int m, int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-
 struct TcParams {
     const float* in_scale;   // [n, ci]
     const float* out_scale;  // [n, co]
@@ -126,15 +52,6 @@ struct TcParams {
     int act;
     float alpha, gain;
 };
-
-// split two floats into packed bf16x2 hi and lo words (element 0 in the low half)
-__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    float2 hf = __bfloat1622float2(h);
-    __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
-    hi = *reinterpret_cast<uint32_t*>(&h);
-    lo = *reinterpret_cast<uint32_t*>(&l);
-}
 
 template <int BN>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
@@ -296,16 +213,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_fwd_tc_kernel(const __grid_c
             uint32_t acc[16];
             tmem_ld16(tmem_d + ((uint32_t)(q4 * 32) << 16) + (uint32_t)col0, acc);
             if (e_ok) {
+                float u[CW];
+                float umax = 0.f;
+#pragma unroll
+                for (int j = 0; j < CW; ++j) {
+                    const int co = n0 + col0 + j;
+                    float val = __uint_as_float(acc[j]);
+                    if (p.out_scale) val *= __ldg(p.out_scale + (long long)eb * p.co + co);
+                    if (p.bias) val += __ldg(p.bias + co);
+                    val += nz;
+                    u[j] = val;
+                    umax = fmaxf(umax, fabsf(val));
+                }
 #pragma unroll
                 for (int j = 0; j < CW; j += 4) {
                     float o[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const int co = n0 + col0 + j + e;
-                        float val = __uint_as_float(acc[j + e]);
-                        if (p.out_scale) val *= __ldg(p.out_scale + (long long)eb * p.co + co);
-                        if (p.bias) val += __ldg(p.bias + co);
-                        val += nz;
+                        float val = u[j + e];
                         if (p.act == 3) val = val > 0.f ? val : val * p.alpha;
                         o[e] = val * p.gain;
                     }
@@ -376,21 +301,6 @@ static bool geometry(int n, int h, int w, int ci, int co, int k, Geometry& g) {
     g.ksteps = (g.subs + 1) / 2;
     (void)n;
     return true;
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)ptr;
-    }
-    return fn;
 }
 
 }  // namespace tc
@@ -466,8 +376,5 @@ int conv_fwd_tc(const ConvParams& p, cudaStream_t st) {
     if (g.bn == 64) return launch_fwd<64>(map, tp, grid, st);
     return launch_fwd<32>(map, tp, grid, st);
 }
-
-bool wgrad_tc_supported(int, int, int, int, int, int) { return false; }
-int conv_wgrad_tc(WgradParams, int, cudaStream_t) { return fail(SG2_ENOTSUP, "conv_wgrad_tc: not built yet"); }
 
 }  // namespace sg2

@@ -17,7 +17,7 @@ import torch
 
 from .. import _lib
 
-IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
+IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC32 = 0, 1, 2, 3
 _default_impl = IMPL_AUTO
 
 # bench.py sets this to a list to time every convolution launch with CUDA events on the launching stream:
@@ -42,9 +42,10 @@ class _timed:
 
 
 def set_default_impl(impl: int) -> None:
-    """0 = auto (tcgen05 where supported, else fp32 SIMT), 1 = force SIMT, 2 = force tcgen05."""
+    """0 = auto (tcgen05 where the shape allows -- fp32-class tf32x3 for forward convs, bf16x3 for gradients --
+    else fp32 SIMT), 1 = SIMT everywhere, 2 = prefer bf16x3 for every conv, 3 = prefer tf32x3 for every conv."""
     global _default_impl
-    assert impl in (0, 1, 2)
+    assert impl in (0, 1, 2, 3)
     _default_impl = impl
 
 
@@ -78,16 +79,26 @@ def _pack(w: torch.Tensor, coef: float, transpose: bool, impl: int) -> torch.Ten
 
 
 def _conv_raw(x, w, coef, transpose, in_scale=None, out_scale=None, bias=None, noise=None,
-              slope=None, out_nchw=False, impl=None):
+              slope=None, out_nchw=False, impl=None, precise=None):
     """One library call: y = act(out_scale * conv(x * in_scale, w*coef) + bias + noise).
 
-    transpose=True runs the data-gradient conv (x has w.shape[0] channels, y has w.shape[1])."""
+    transpose=True runs the data-gradient conv (x has w.shape[0] channels, y has w.shape[1]).
+    precise: fp32-class tensor-core kernel (tf32x3 + promotion) instead of bf16x3.  Default: yes for forward
+    convolutions (their outputs decide leaky-ReLU signs), no for data gradients."""
+    strict = impl is not None                      # an explicit request must be honoured or fail loudly
     impl = _default_impl if impl is None else impl
     _lib.require_cuda(x, w)
     lib = _lib.load()
     co, ci, k, _ = w.shape
     cin, cout = (co, ci) if transpose else (ci, co)
     n, cx, h, wd = x.shape
+    precise = (not transpose) if precise is None else precise
+    req = impl
+    impl = lib.sg2_conv2d_select_impl(n, h, wd, cin, cout, k, req, 1 if precise else 0)
+    if impl < 0 and not strict:
+        impl = IMPL_SIMT                            # a global tensor-core preference falls back to the fp32 SIMT kernel
+    if impl < 0:
+        raise RuntimeError(f'conv2d: implementation {req} does not take n={n} h={h} w={wd} ci={cin} co={cout} k={k}')
     if cx != cin:
         raise RuntimeError(f'conv2d: input has {cx} channels, weight expects {cin}')
     if x.dtype != torch.float32 or w.dtype != torch.float32:
@@ -110,7 +121,8 @@ def _conv_raw(x, w, coef, transpose, in_scale=None, out_scale=None, bias=None, n
 
 
 def _wgrad_raw(x, gy, k, coef, in_scale=None, out_scale=None, impl=None):
-    impl = _default_impl if impl is None else impl
+    if impl is None:
+        impl = IMPL_SIMT if _default_impl == IMPL_SIMT else IMPL_AUTO
     _lib.require_cuda(x, gy)
     lib = _lib.load()
     n, ci, h, wd = x.shape
@@ -133,10 +145,10 @@ class Conv2dFn(torch.autograd.Function):
     """y = conv2d(x, w * coef), stride 1, same padding."""
 
     @staticmethod
-    def forward(ctx, x, w, coef):
+    def forward(ctx, x, w, coef, precise=True):
         ctx.coef = coef
         ctx.save_for_backward(x, w)
-        return _conv_raw(x, w, coef, False)
+        return _conv_raw(x, w, coef, False, precise=precise)
 
     @staticmethod
     def backward(ctx, gy):
@@ -146,7 +158,7 @@ class Conv2dFn(torch.autograd.Function):
             gx = Conv2dTransposeFn.apply(gy, w, ctx.coef)
         if ctx.needs_input_grad[1]:
             gw = Conv2dWgradFn.apply(x, gy, w.shape[2], ctx.coef)
-        return gx, gw, None
+        return gx, gw, None, None
 
 
 class Conv2dTransposeFn(torch.autograd.Function):
@@ -163,7 +175,7 @@ class Conv2dTransposeFn(torch.autograd.Function):
         gy, w = ctx.saved_tensors
         ggy = gw = None
         if ctx.needs_input_grad[0]:
-            ggy = Conv2dFn.apply(g, w, ctx.coef)
+            ggy = Conv2dFn.apply(g, w, ctx.coef, False)       # a gradient quantity: bf16x3 is enough
         if ctx.needs_input_grad[1]:
             gw = Conv2dWgradFn.apply(g, gy, w.shape[2], ctx.coef)
         return ggy, gw, None
@@ -185,13 +197,13 @@ class Conv2dWgradFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = Conv2dTransposeFn.apply(gy, gdw, ctx.coef)
         if ctx.needs_input_grad[1]:
-            ggy = Conv2dFn.apply(x, gdw, ctx.coef)
+            ggy = Conv2dFn.apply(x, gdw, ctx.coef, False)
         return gx, ggy, None, None
 
 
 def conv2d(x, w, coef: float = 1.0):
     """Drop-in for ``conv2d_gradfix.conv2d(x, w*coef, padding=k//2)`` (stride 1, odd k)."""
-    return Conv2dFn.apply(x, w, float(coef))
+    return Conv2dFn.apply(x, w, float(coef), True)
 
 
 # ----------------------------------------------------------------------------------------------
