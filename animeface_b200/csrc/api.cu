@@ -6,12 +6,16 @@ namespace sg2 {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 
-// impl codes: 0 auto, 1 fp32 SIMT, 2 tcgen05 bf16x3, 3 tcgen05 tf32x3 + promotion (fp32-class; forward convs).
+// impl codes: 0 auto, 1 fp32 SIMT, 2 tcgen05 bf16x3 (per-tap loads), 3 tcgen05 tf32x3+promotion (per-tap loads),
+// 4 tcgen05 bf16x3 halo kernel, 5 tcgen05 tf32x3+promotion halo kernel.  `precise` steers auto towards 3/5.
 // Returns the implementation that will run, or -1 when an explicitly requested one does not take the shape.
 static int resolve_impl(int impl, int precise, int n, int h, int w, int ci, int co, int k) {
     const bool tc_ok = conv_tc_supported(n, h, w, ci, co, k);
+    const bool halo_ok = conv_halo_supported(n, h, w, ci, co, k);
     if (impl == 1) return 1;
     if (impl == 2 || impl == 3) return tc_ok ? impl : -1;
+    if (impl == 4 || impl == 5) return halo_ok ? impl : -1;
+    if (halo_ok) return precise ? 5 : 4;
     return tc_ok ? (precise ? 3 : 2) : 1;
 }
 }  // namespace sg2
@@ -27,7 +31,7 @@ extern "C" int64_t sg2_launch_count(void) { return (int64_t)g_launches.load(); }
 struct PackHeader { int impl, transpose, co, ci; };
 
 extern "C" int sg2_conv2d_select_impl(int n, int h, int w, int ci, int co, int k, int impl, int precise) {
-    if (n <= 0 || h <= 0 || w <= 0 || ci <= 0 || co <= 0 || (k != 1 && k != 3) || impl < 0 || impl > 3) return SG2_EINVAL;
+    if (n <= 0 || h <= 0 || w <= 0 || ci <= 0 || co <= 0 || (k != 1 && k != 3) || impl < 0 || impl > 5) return SG2_EINVAL;
     const int r = resolve_impl(impl, precise, n, h, w, ci, co, k);
     return r < 0 ? SG2_ENOTSUP : r;
 }
@@ -37,9 +41,11 @@ extern "C" int64_t sg2_conv2d_packed_size(int co, int ci, int k, int impl) {
     long long simt = (long long)co * ci * k * k * 4;
     long long tcb = conv_packed_bytes_tc(co, ci, k);
     long long tc32 = conv_packed_bytes_tc32(co, ci, k);
+    long long hl = conv_packed_bytes_halo(co, ci, k);
     (void)impl;
     long long m = simt > tcb ? simt : tcb;
-    return 256 + (m > tc32 ? m : tc32);
+    m = m > tc32 ? m : tc32;
+    return 256 + (m > hl ? m : hl);
 }
 
 static int pick_impl_for_pack(int co, int ci, int k, int transpose, int impl) {
@@ -64,6 +70,7 @@ extern "C" int sg2_conv2d_pack_weight(const float* w, void* packed, int co, int 
     void* body = (char*)packed + 256;
     if (use == 1) return conv_pack_simt(w, (float*)body, co, ci, k, coef, transpose, st);
     if (use == 3) return conv_pack_tc32(w, body, co, ci, k, coef, transpose, st);
+    if (use == 4 || use == 5) return conv_pack_halo(w, body, co, ci, k, coef, transpose, use == 5, st);
     return conv_pack_tc(w, body, co, ci, k, coef, transpose, st);
 }
 
@@ -92,6 +99,7 @@ extern "C" int sg2_conv2d_fwd(const float* x, const void* packed_w, float* y, co
     cudaStream_t st = (cudaStream_t)stream;
     if (packed_for == 2) return conv_fwd_tc(p, st);
     if (packed_for == 3) return conv_fwd_tc32(p, st);
+    if (packed_for == 4 || packed_for == 5) return conv_fwd_halo(p, packed_for == 5, st);
     return conv_fwd_simt(p, st);
 }
 

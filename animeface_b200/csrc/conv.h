@@ -47,4 +47,10 @@ int conv_fwd_tc32(const ConvParams& p, cudaStream_t st);
 int conv_pack_tc32(const float* w, void* wp, int co, int ci, int k, float coef, int transpose, cudaStream_t st);
 long long conv_packed_bytes_tc32(int co, int ci, int k);
 
+// tcgen05 path, halo variant (conv_halo.cu): patch loaded/converted once per tile, taps = shifted descriptor windows
+bool conv_halo_supported(int n, int h, int w, int ci, int co, int k);
+int conv_fwd_halo(const ConvParams& p, int precise, cudaStream_t st);
+int conv_pack_halo(const float* w, void* wp, int co, int ci, int k, float coef, int transpose, int precise, cudaStream_t st);
+long long conv_packed_bytes_halo(int co, int ci, int k);
+
 }  // namespace sg2

@@ -1,0 +1,454 @@
+// tcgen05 implicit-GEMM convolution, "halo" variant: the activation patch of a tile is loaded and converted ONCE and
+// the k*k taps are shifted windows of it, addressed through the UMMA shared-memory descriptors.
+//
+// conv_tc.cu / conv_tc32.cu load one TMA box per (tap, channel block): every input element crosses L2->SMEM and the
+// fp32->split conversion 9 times for a 3x3 kernel, which makes the low-channel, high-resolution layers of the path
+// (64->64 @256^2 etc.) L2- and conversion-bound.  Here, per CTA tile of 8 x 16 pixels and per block of input channels:
+//   TMA      one box [32 ch, 8+2p, 16+2p, 1] (p = k/2; out-of-bounds -> 0 = zero padding) into a SWIZZLE_128B fp32 slot
+//   xform    8 warps: (style scale) -> split planes, written as a NON-swizzled K-major operand image
+//            plane[chunk c][patch row r][16 B]   (chunk = 16 B of K; LBO = rows*16 B between chunks, 16 B between rows)
+//   MMA      tap (dy,dx), K chunk pair kq: A descriptor start = plane + 2kq*LBO + ((dy+p)*PW + dx+p)*16, SBO = PW*16
+//            (an 8-pixel tile row is an 8-row core-matrix group, consecutive tile rows are PW patch rows apart), so
+//            all taps read the same converted patch; B = pre-packed weight tile of (tap, channel block), SWIZZLE_128B.
+// PRECISE = false: bf16x3 (hi/lo planes, kind::f16, 64 channels per block)           -> data gradients
+// PRECISE = true : tf32x3 + promotion (big/small planes, kind::tf32, 32 channels per block, TMEM accumulator promoted to
+//                  fp32 registers every 2 taps = 8 big*big MMAs)                      -> forward convs, fp32-class
+// Persistent CTAs (one per SM), double-buffered planes and TMEM accumulators, dedicated epilogue warps.
+// Warp roles: 0 patch TMA, 1 MMA (+TMEM alloc), 2..9 transform, 10.. epilogue/promotion, last = weight TMA.
+#include "tc_common.cuh"
+#include "conv.h"
+
+namespace sg2 {
+namespace halo {
+using namespace tc;
+
+constexpr int TW = 8, TH = 16, BM = 128;
+constexpr int SLOT = 23 * 1024 + 512;      // one fp32 box: up to 180 rows x 128 B = 23040 B, padded to a 1024 multiple + slack
+constexpr int SLOT_BYTES = 24 * 1024;      // 1024-aligned slot pitch
+constexpr int MAX_ROWS = (TW + 2) * (TH + 2);            // 180 patch rows
+constexpr int PLANE = 8 * MAX_ROWS * 16;                 // 8 chunks x rows x 16 B = 23040 B
+constexpr int PLANE_PITCH = 23 * 1024;                   // 23552
+constexpr int BSTAGES = 3;
+
+template <int BN, bool PRECISE> struct Cfg {
+    static constexpr int EPI_WARPS = PRECISE ? 8 : 4;
+    static constexpr int NWARPS = 10 + EPI_WARPS + 1;
+    static constexpr int NTHREADS = NWARPS * 32;
+    static constexpr int BWARP = NWARPS - 1;                       // weight producer warp
+    static constexpr int KB = PRECISE ? 32 : 64;                   // input channels per block (128 B of K per operand row)
+    static constexpr int BOXES = PRECISE ? 1 : 2;                  // TMA boxes (32 ch) per block
+    static constexpr int SLOTS = BN == 128 ? 1 : 2;                // staging slots (boxes in flight); 1 keeps BN=128 under 227 KB
+    static constexpr int BTILE = 2 * BN * 128;                     // two planes of [BN rows x 128 B]
+    static constexpr int SMEM = 1024 + SLOTS * SLOT_BYTES + 2 * 2 * PLANE_PITCH + BSTAGES * BTILE + 256;
+    static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+};
+
+struct Params {
+    const float* in_scale; const float* out_scale; const float* bias; const float* noise;
+    float* y;
+    long long ys[4];
+    const unsigned char* wp;
+    int n, h, w, ci, co, k;
+    int tiles_x, tiles_y, m_tiles, n_tiles;
+    int nkb;                 // channel blocks
+    int act;
+    float alpha, gain;
+};
+
+// non-swizzled K-major descriptor: LBO between 16-byte K chunks, SBO between 8-row groups, 16 B between rows
+__device__ __forceinline__ uint64_t interleave_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46);
+}
+
+template <int BN, bool PRECISE>
+__global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
+    using C = Cfg<BN, PRECISE>;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t slot_base = base;
+    const uint32_t plane_base = slot_base + C::SLOTS * SLOT_BYTES;            // [buf][plane]
+    const uint32_t b_base = plane_base + 4 * PLANE_PITCH;
+    const uint32_t bar_base = b_base + BSTAGES * C::BTILE;
+    auto st_full = [&](int s) { return bar_base + 8u * s; };                  // 2
+    auto st_empty = [&](int s) { return bar_base + 16u + 8u * s; };           // 2
+    auto pl_full = [&](int b) { return bar_base + 32u + 8u * b; };            // 2
+    auto pl_empty = [&](int b) { return bar_base + 48u + 8u * b; };           // 2
+    auto b_full = [&](int s) { return bar_base + 64u + 8u * s; };             // 3
+    auto b_empty = [&](int s) { return bar_base + 88u + 8u * s; };            // 3
+    auto acc_full = [&](int b) { return bar_base + 112u + 8u * b; };          // 2
+    auto acc_empty = [&](int b) { return bar_base + 128u + 8u * b; };         // 2
+    const uint32_t tmem_slot = bar_base + 144u;
+    auto plane = [&](int buf, int pl) { return plane_base + (uint32_t)((buf * 2 + pl) * PLANE_PITCH); };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pad = p.k >> 1, taps = p.k * p.k;
+    const int PW = TW + 2 * pad, PH = TH + 2 * pad, PR = PW * PH;
+    const uint32_t LBO = (uint32_t)PR * 16u, SBO = (uint32_t)PW * 16u;
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    auto tile_coords = [&](int tile, int& x0, int& y0, int& b0, int& n0) {
+        const int nt = tile / p.m_tiles, mt = tile % p.m_tiles;
+        x0 = (mt % p.tiles_x) * TW;
+        y0 = ((mt / p.tiles_x) % p.tiles_y) * TH;
+        b0 = mt / (p.tiles_x * p.tiles_y);
+        n0 = nt * BN;
+    };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(st_full(s), 1); mbar_init(st_empty(s), 8);
+            mbar_init(pl_full(s), 8); mbar_init(pl_empty(s), 1);
+            mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), C::EPI_WARPS);
+        }
+        for (int s = 0; s < BSTAGES; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_d;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_d) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ================= patch producer: one TMA box per (tile, channel block, 32-channel half) =================
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+            int bx = 0;                                   // global box counter
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int x0, y0, b0, n0;
+                tile_coords(tile, x0, y0, b0, n0);
+                for (int kb = 0; kb < p.nkb; ++kb)
+                    for (int hb = 0; hb < C::BOXES; ++hb, ++bx) {
+                        const int s = bx % C::SLOTS;
+                        mbar_wait(st_empty(s), ((bx / C::SLOTS) & 1) ^ 1);
+                        mbar_expect_tx(st_full(s), (uint32_t)PR * 128u);
+                        tma_load_4d(slot_base + s * SLOT_BYTES, &xmap, st_full(s), kb * C::KB + 32 * hb, x0 - pad, y0 - pad, b0);
+                    }
+            }
+        }
+    } else if (warp == C::BWARP) {
+        // ================= weight producer: one pre-packed tile per (tile, channel block, tap) =================
+        if (lane == 0) {
+            int bt = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = tile / p.m_tiles;
+                const unsigned char* wsrc = p.wp + (size_t)nt * p.nkb * taps * C::BTILE;
+                for (int i = 0; i < p.nkb * taps; ++i, ++bt) {
+                    const int s = bt % BSTAGES;
+                    mbar_wait(b_empty(s), ((bt / BSTAGES) & 1) ^ 1);
+                    mbar_expect_tx(b_full(s), C::BTILE);
+                    bulk_load(b_base + s * C::BTILE, wsrc + (size_t)i * C::BTILE, C::BTILE, b_full(s));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = PRECISE ? idesc_tf32(BM, BN) : idesc_bf16(BM, BN);
+            int bt = 0, kbg = 0, sg = 0;                  // global weight-tile / channel-block / accumulator-segment counters
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int f = 0;                                // flat (kb, tap) index inside the tile
+                for (int kb = 0; kb < p.nkb; ++kb, ++kbg) {
+                    const int pbuf = kbg & 1;
+                    mbar_wait(pl_full(pbuf), (kbg >> 1) & 1);
+                    for (int t = 0; t < taps; ++t, ++bt, ++f) {
+                        // accumulator segment: PRECISE -> every 2 taps, else the whole tile
+                        const bool seg_start = PRECISE ? ((f & 1) == 0) : (f == 0);
+                        const bool seg_end = PRECISE ? ((f & 1) == 1 || f == p.nkb * taps - 1) : (f == p.nkb * taps - 1);
+                        const int abuf = sg & 1;
+                        if (seg_start) mbar_wait(acc_empty(abuf), ((sg >> 1) & 1) ^ 1);
+                        const int s = bt % BSTAGES;
+                        mbar_wait(b_full(s), (bt / BSTAGES) & 1);
+                        tc_fence_after();
+                        const uint32_t d = tmem_d + (uint32_t)(abuf * BN);
+                        const int dy = t / p.k, dx = t % p.k;                      // already offset by +pad
+                        const uint32_t arow = (uint32_t)(dy * PW + dx) * 16u;
+                        const uint32_t a0 = plane(pbuf, 0) + arow, a1 = plane(pbuf, 1) + arow;
+                        const uint32_t b0_ = b_base + s * C::BTILE, b1_ = b0_ + BN * 128;
+#pragma unroll
+                        for (int kq = 0; kq < 4; ++kq) {
+                            const uint64_t da0 = interleave_desc(a0 + 2 * kq * LBO, LBO, SBO), da1 = interleave_desc(a1 + 2 * kq * LBO, LBO, SBO);
+                            const uint64_t db0 = kmajor_desc(b0_ + kq * 32), db1 = kmajor_desc(b1_ + kq * 32);
+                            const uint32_t accum = !(seg_start && kq == 0);
+                            if (PRECISE) {
+                                mma_tf32(d, da0, db0, idesc, accum); mma_tf32(d, da1, db0, idesc, 1); mma_tf32(d, da0, db1, idesc, 1);
+                            } else {
+                                mma_bf16(d, da0, db0, idesc, accum); mma_bf16(d, da1, db0, idesc, 1); mma_bf16(d, da0, db1, idesc, 1);
+                            }
+                        }
+                        mma_commit(b_empty(s));
+                        if (seg_end) { mma_commit(acc_full(abuf)); ++sg; }
+                    }
+                    mma_commit(pl_empty(pbuf));
+                }
+            }
+        }
+    } else if (warp < 10) {
+        // ================= transform: fp32 box -> split planes (non-swizzled K-major) =================
+        const int tt = threadIdx.x - 64;                  // 0..255
+        int bx = 0, kbg = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int x0, y0, b0, n0;
+            tile_coords(tile, x0, y0, b0, n0);
+            for (int kb = 0; kb < p.nkb; ++kb, ++kbg) {
+                const int pbuf = kbg & 1;
+                const uint32_t pl0 = plane(pbuf, 0), pl1 = plane(pbuf, 1);
+                bool waited = false;
+                for (int hb = 0; hb < C::BOXES; ++hb, ++bx) {
+                    const int s = bx % C::SLOTS;
+                    mbar_wait(st_full(s), (bx / C::SLOTS) & 1);
+                    if (!waited) { mbar_wait(pl_empty(pbuf), ((kbg >> 1) & 1) ^ 1); waited = true; }
+                    const uint32_t src0 = slot_base + s * SLOT_BYTES;
+                    const int cbase = kb * C::KB + 32 * hb;                      // first channel of this box
+                    // items = (row, 16-channel half); consecutive lanes take consecutive rows -> conflict-free both ways
+                    for (int item = tt; item < 2 * PR; item += 256) {
+                        const int half = item >= PR ? 1 : 0, r = item - half * PR;
+                        const uint32_t src = src0 + (uint32_t)r * 128u;
+                        const int sw = r & 7;
+                        float v[16];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 t4 = lds4(src + (uint32_t)(((4 * half + q) ^ sw) << 4));
+                            v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
+                        }
+                        if (p.in_scale) {
+                            const int c = cbase + 16 * half;
+                            if (c < p.ci) {
+                                const float* sp = p.in_scale + (long long)b0 * p.ci + c;
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float4 t4 = ldg4(sp + 4 * q);
+                                    v[4 * q] *= t4.x; v[4 * q + 1] *= t4.y; v[4 * q + 2] *= t4.z; v[4 * q + 3] *= t4.w;
+                                }
+                            }
+                        }
+                        if (PRECISE) {
+                            // 16 channels = 4 chunks of 4 tf32; chunk index within the 32-channel block = 4*half + q
+                            uint32_t g[16], sm[16];
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) { g[e] = rna_tf32(v[e]); sm[e] = rna_tf32(v[e] - __uint_as_float(g[e])); }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const uint32_t off = (uint32_t)(4 * half + q) * LBO + (uint32_t)r * 16u;
+                                sts4(pl0 + off, g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]);
+                                sts4(pl1 + off, sm[4 * q], sm[4 * q + 1], sm[4 * q + 2], sm[4 * q + 3]);
+                            }
+                        } else {
+                            // 16 channels = 2 chunks of 8 bf16; chunk index within the 64-channel block = 4*hb + 2*half + q
+                            uint32_t hi[8], lo[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) split2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) {
+                                const uint32_t off = (uint32_t)(4 * hb + 2 * half + q) * LBO + (uint32_t)r * 16u;
+                                sts4(pl0 + off, hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+                                sts4(pl1 + off, lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(st_empty(s));
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(pl_full(pbuf));
+            }
+        }
+    } else {
+        // ================= epilogue warps (PRECISE: promotion of every segment, then epilogue) =================
+        const int ew = warp - 10;
+        const int q4 = warp & 3;
+        const int er = q4 * 32 + lane;                    // accumulator row = pixel (y*8 + x)
+        constexpr int COLS = PRECISE ? BN / 2 : BN;        // columns this thread owns
+        const int cstart = PRECISE ? (ew >> 2) * COLS : 0;
+        const int nflat = p.nkb * taps;
+        const int nseg = PRECISE ? (nflat + 1) / 2 : 1;
+        int sg = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int x0, y0, b0, n0;
+            tile_coords(tile, x0, y0, b0, n0);
+            const int ex = x0 + (er & 7), ey = y0 + (er >> 3);
+            const long long pix = ((long long)b0 * p.h + ey) * p.w + ex;
+            const float nz = p.noise ? __ldg(p.noise + pix) : 0.f;
+            float* yrow = p.y + (long long)b0 * p.ys[0] + (long long)ey * p.ys[2] + (long long)ex * p.ys[3];
+            float racc[PRECISE ? COLS : 1];
+            if (PRECISE) {
+#pragma unroll
+                for (int j = 0; j < COLS; ++j) racc[j] = 0.f;
+                for (int seg = 0; seg < nseg - 1; ++seg, ++sg) {
+                    const int abuf = sg & 1;
+                    mbar_wait(acc_full(abuf), (sg >> 1) & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int c = 0; c < COLS / 16; ++c) {
+                        uint32_t v[16];
+                        tmem_ld16(tmem_d + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(abuf * BN + cstart + c * 16), v);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) racc[c * 16 + j] += __uint_as_float(v[j]);
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty(abuf));
+                }
+            }
+            // last (or only) segment: read, finish, store
+            const int abuf = sg & 1;
+            mbar_wait(acc_full(abuf), (sg >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < COLS / 16; ++c) {
+                uint32_t v[16];
+                tmem_ld16(tmem_d + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(abuf * BN + cstart + c * 16), v);
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    float o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int co = n0 + cstart + c * 16 + j + e;
+                        float val = __uint_as_float(v[j + e]);
+                        if (PRECISE) val += racc[(PRECISE ? c * 16 + j + e : 0)];
+                        if (p.out_scale) val *= __ldg(p.out_scale + (long long)b0 * p.co + co);
+                        if (p.bias) val += __ldg(p.bias + co);
+                        val += nz;
+                        if (p.act == 3) val = val > 0.f ? val : val * p.alpha;
+                        o[e] = val * p.gain;
+                    }
+                    const int cb = n0 + cstart + c * 16 + j;
+                    if (p.ys[1] == 1) st4(yrow + cb, make_float4(o[0], o[1], o[2], o[3]));
+                    else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) yrow[(long long)(cb + e) * p.ys[1]] = o[e];
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty(abuf));
+            ++sg;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_d, C::TMEM_COLS);
+    }
+}
+
+// w[co][ci][k][k] -> per (n-tile, channel block, tap): two planes of [bn rows x 128 B], SWIZZLE_128B, zero beyond ci
+__global__ void conv_pack_halo_kernel(const float* __restrict__ w, unsigned char* __restrict__ wp, int co, int ci, int k,
+                                      float coef, int transpose, int bn, int nkb, int kbs, int precise) {
+    const int cin = transpose ? co : ci, nout_n = transpose ? ci : co;
+    const int kk2 = k * k;
+    const long long total = (long long)(nout_n / bn) * nkb * kk2 * bn * kbs;
+    const size_t btile = (size_t)2 * bn * 128;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int kk = (int)(idx % kbs);
+        long long r = idx / kbs;
+        const int nl = (int)(r % bn); r /= bn;
+        const int t = (int)(r % kk2); r /= kk2;
+        const int kb = (int)(r % nkb);
+        const int nt = (int)(r / nkb);
+        const int kin = kb * kbs + kk, nout = nt * bn + nl;
+        float v = 0.f;
+        if (kin < cin) {
+            const int o = transpose ? kin : nout, i = transpose ? nout : kin, ts = transpose ? kk2 - 1 - t : t;
+            v = w[((long long)o * ci + i) * kk2 + ts] * coef;
+        }
+        unsigned char* tile = wp + (((size_t)nt * nkb + kb) * kk2 + t) * btile;
+        const int esz = precise ? 4 : 2;
+        const size_t off = (size_t)nl * 128 + ((((kk * esz) >> 4) ^ (nl & 7)) << 4) + ((kk * esz) & 15);
+        if (precise) {
+            const uint32_t big = rna_tf32(v), small = rna_tf32(v - __uint_as_float(big));
+            *reinterpret_cast<uint32_t*>(tile + off) = big;
+            *reinterpret_cast<uint32_t*>(tile + (size_t)bn * 128 + off) = small;
+        } else {
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+            *reinterpret_cast<__nv_bfloat16*>(tile + off) = h;
+            *reinterpret_cast<__nv_bfloat16*>(tile + (size_t)bn * 128 + off) = l;
+        }
+    }
+}
+
+static int pick_bn(int co) { return co % 128 == 0 ? 128 : (co == 64 ? 64 : (co == 32 ? 32 : 0)); }
+
+template <int BN, bool PRECISE>
+static int launch(const CUtensorMap& map, const Params& tp, dim3 grid, cudaStream_t st) {
+    using C = Cfg<BN, PRECISE>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e != cudaSuccess) return fail(SG2_ELAUNCH, "conv_halo: cannot opt in to %d B of shared memory: %s", C::SMEM, cudaGetErrorString(e));
+        configured = true;
+    }
+    conv_halo_kernel<BN, PRECISE><<<grid, C::NTHREADS, C::SMEM, st>>>(map, tp);
+    return launched(PRECISE ? "conv_halo_tf32x3" : "conv_halo_bf16x3");
+}
+
+}  // namespace halo
+
+bool conv_halo_supported(int n, int h, int w, int ci, int co, int k) {
+    (void)n;
+    if (k != 1 && k != 3) return false;
+    if (ci % 32 != 0 || ci < 32) return false;
+    if (!halo::pick_bn(co)) return false;
+    return (w % halo::TW) == 0 && (h % halo::TH) == 0 && w <= 4096 && h <= 4096;
+}
+
+long long conv_packed_bytes_halo(int co, int ci, int k) {
+    long long best = 0;
+    for (int tr = 0; tr < 2; ++tr) {
+        const int cin = tr ? co : ci, cout = tr ? ci : co;
+        const int bn = halo::pick_bn(cout);
+        if (!bn || cin % 32) continue;
+        const long long nkb32 = (cin + 31) / 32;              // precise: 32-channel blocks (the larger of the two packs)
+        const long long b = (long long)(cout / bn) * nkb32 * k * k * 2 * bn * 128;
+        if (b > best) best = b;
+    }
+    return best;
+}
+
+int conv_pack_halo(const float* w, void* wp, int co, int ci, int k, float coef, int transpose, int precise, cudaStream_t st) {
+    const int cin = transpose ? co : ci, cout = transpose ? ci : co;
+    const int bn = halo::pick_bn(cout);
+    if (!bn || cin % 32) return fail(SG2_ENOTSUP, "conv_pack_halo: unsupported shape");
+    const int kbs = precise ? 32 : 64;
+    const int nkb = (cin + kbs - 1) / kbs;
+    const long long total = (long long)(cout / bn) * nkb * k * k * bn * kbs;
+    const int blocks = (int)std::min<long long>(ceil_div(total, 256), (long long)num_sms() * 8);
+    halo::conv_pack_halo_kernel<<<blocks, 256, 0, st>>>(w, (unsigned char*)wp, co, ci, k, coef, transpose, bn, nkb, kbs, precise);
+    return launched("conv_pack_halo");
+}
+
+int conv_fwd_halo(const ConvParams& p, int precise, cudaStream_t st) {
+    if (!conv_halo_supported(p.n, p.h, p.w, p.ci, p.co, p.k)) return fail(SG2_ENOTSUP, "conv_fwd_halo: unsupported shape");
+    const int pad = p.k >> 1;
+    CUtensorMap map;
+    int rc = tc::make_nhwc_map(&map, p.x, p.n, p.h, p.w, p.ci, halo::TW + 2 * pad, halo::TH + 2 * pad, 1, "conv_fwd_halo");
+    if (rc) return rc;
+    halo::Params tp;
+    tp.in_scale = p.in_scale; tp.out_scale = p.out_scale; tp.bias = p.bias; tp.noise = p.noise;
+    tp.y = p.y;
+    for (int i = 0; i < 4; ++i) tp.ys[i] = p.ys[i];
+    tp.wp = (const unsigned char*)p.wp;
+    tp.n = p.n; tp.h = p.h; tp.w = p.w; tp.ci = p.ci; tp.co = p.co; tp.k = p.k;
+    tp.tiles_x = p.w / halo::TW; tp.tiles_y = p.h / halo::TH;
+    tp.m_tiles = tp.tiles_x * tp.tiles_y * p.n;
+    const int bn = halo::pick_bn(p.co);
+    tp.n_tiles = p.co / bn;
+    const int kbs = precise ? 32 : 64;
+    tp.nkb = (p.ci + kbs - 1) / kbs;
+    tp.act = p.act; tp.alpha = p.alpha; tp.gain = p.gain;
+    dim3 grid((unsigned)std::min(tp.m_tiles * tp.n_tiles, num_sms()));
+    if (precise) {
+        if (bn == 128) return halo::launch<128, true>(map, tp, grid, st);
+        if (bn == 64) return halo::launch<64, true>(map, tp, grid, st);
+        return halo::launch<32, true>(map, tp, grid, st);
+    }
+    if (bn == 128) return halo::launch<128, false>(map, tp, grid, st);
+    if (bn == 64) return halo::launch<64, false>(map, tp, grid, st);
+    return halo::launch<32, false>(map, tp, grid, st);
+}
+
+}  // namespace sg2

@@ -30,7 +30,7 @@ constexpr int BM = 128;            // pixels per CTA tile (UMMA M)
 constexpr int KSTEP = 64;          // k-columns per pipeline step (bf16: 128 B rows)
 constexpr int SUB = 32;            // channels per TMA box (fp32: 128 B rows)
 constexpr int STAGES = 2;
-constexpr int NTHREADS = 320;      // 10 warps
+constexpr int NTHREADS = 448;      // 14 warps: TMA, MMA, 8 transform, 4 epilogue
 constexpr int STAGE_F32 = 2 * BM * SUB * 4;      // 32 KB: two fp32 sub-block tiles
 constexpr int STAGE_A = 2 * BM * KSTEP * 2;      // 32 KB: A_hi + A_lo
 
@@ -47,7 +47,7 @@ struct TcParams {
     const unsigned char* wp; // packed weights
     int n, h, w, ci, co, k;
     int tw, th, tb;          // pixel box of one CTA tile (tw*th*tb == 128)
-    int tiles_x, tiles_y;
+    int tiles_x, tiles_y, m_tiles, n_tiles;
     int ksteps, subs, spb;   // K steps, real sub-blocks, sub-blocks per tap
     int act;
     float alpha, gain;
@@ -62,24 +62,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_fwd_tc_kernel(const __grid_c
     const uint32_t a_base = f32_base + STAGES * STAGE_F32;
     const uint32_t b_base = a_base + STAGES * STAGE_A;
     const uint32_t bar_base = b_base + STAGES * stage_b(BN);
-    // barriers (8 B each): f_full[2] f_empty[2] a_full[2] a_empty[2] b_full[2] b_empty[2] acc_full tmem_slot
     auto f_full = [&](int s) { return bar_base + 8u * s; };
     auto f_empty = [&](int s) { return bar_base + 16u + 8u * s; };
     auto a_full = [&](int s) { return bar_base + 32u + 8u * s; };
     auto a_empty = [&](int s) { return bar_base + 48u + 8u * s; };
     auto b_full = [&](int s) { return bar_base + 64u + 8u * s; };
     auto b_empty = [&](int s) { return bar_base + 80u + 8u * s; };
-    const uint32_t acc_full = bar_base + 96u;
-    const uint32_t tmem_slot = bar_base + 104u;
+    auto acc_full = [&](int b) { return bar_base + 96u + 8u * b; };
+    auto acc_empty = [&](int b) { return bar_base + 112u + 8u * b; };
+    const uint32_t tmem_slot = bar_base + 128u;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // tile coordinates
-    const int mt = blockIdx.x;
-    const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tbi = mt / (p.tiles_x * p.tiles_y);
-    const int x0 = tx * p.tw, y0 = ty * p.th, b0 = tbi * p.tb;
-    const int n0 = blockIdx.y * BN;
     const int pad = p.k >> 1;
-    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;      // two accumulator buffers: epilogue overlaps the next tile
+    // persistent tile loop: tile = n_tile * m_tiles + m_tile (all CTAs share an n-tile's weights at any time)
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    auto tile_coords = [&](int tile, int& x0, int& y0, int& b0, int& n0) {
+        const int nt = tile / p.m_tiles, mt = tile % p.m_tiles;
+        x0 = (mt % p.tiles_x) * p.tw;
+        y0 = ((mt / p.tiles_x) % p.tiles_y) * p.th;
+        b0 = (mt / (p.tiles_x * p.tiles_y)) * p.tb;
+        n0 = nt * BN;
+    };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -87,7 +91,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_fwd_tc_kernel(const __grid_c
             mbar_init(a_full(s), 8); mbar_init(a_empty(s), 1);
             mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1);
         }
-        mbar_init(acc_full, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 4); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -101,22 +105,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_fwd_tc_kernel(const __grid_c
         // ================= TMA producer =================
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
-            const unsigned char* wsrc = p.wp + (size_t)blockIdx.y * p.ksteps * stage_b(BN);
-            for (int t = 0; t < p.ksteps; ++t) {
-                const int s = t % STAGES;
-                const uint32_t ph = (t / STAGES) & 1;
-                mbar_wait(b_empty(s), ph ^ 1);
-                mbar_expect_tx(b_full(s), stage_b(BN));
-                bulk_load(b_base + s * stage_b(BN), wsrc + (size_t)t * stage_b(BN), stage_b(BN), b_full(s));
-                mbar_wait(f_empty(s), ph ^ 1);
-                mbar_expect_tx(f_full(s), STAGE_F32);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int x0, y0, b0, n0;
+                tile_coords(tile, x0, y0, b0, n0);
+                const unsigned char* wsrc = p.wp + (size_t)(n0 / BN) * p.ksteps * stage_b(BN);
+                for (int t = 0; t < p.ksteps; ++t, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(b_empty(s), ph ^ 1);
+                    mbar_expect_tx(b_full(s), stage_b(BN));
+                    bulk_load(b_base + s * stage_b(BN), wsrc + (size_t)t * stage_b(BN), stage_b(BN), b_full(s));
+                    mbar_wait(f_empty(s), ph ^ 1);
+                    mbar_expect_tx(f_full(s), STAGE_F32);
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int sb = 2 * t + h;
-                    int tap = sb / p.spb, c0 = (sb % p.spb) * SUB;
-                    int dy = tap / p.k - pad, dx = tap % p.k - pad;
-                    if (sb >= p.subs) { c0 = p.ci; dy = 0; dx = 0; }        // K padding: fully out of bounds -> zeros
-                    tma_load_4d(f32_base + s * STAGE_F32 + h * (BM * SUB * 4), &xmap, f_full(s), c0, x0 + dx, y0 + dy, b0);
+                    for (int h = 0; h < 2; ++h) {
+                        const int sb = 2 * t + h;
+                        int tap = sb / p.spb, c0 = (sb % p.spb) * SUB;
+                        int dy = tap / p.k - pad, dx = tap % p.k - pad;
+                        if (sb >= p.subs) { c0 = p.ci; dy = 0; dx = 0; }        // K padding: fully out of bounds -> zeros
+                        tma_load_4d(f32_base + s * STAGE_F32 + h * (BM * SUB * 4), &xmap, f_full(s), c0, x0 + dx, y0 + dy, b0);
+                    }
                 }
             }
         }
@@ -124,126 +133,135 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_fwd_tc_kernel(const __grid_c
         // ================= MMA issuer =================
         if (lane == 0) {
             constexpr uint32_t idesc = idesc_bf16(BM, BN);
-            for (int t = 0; t < p.ksteps; ++t) {
-                const int s = t % STAGES;
-                const uint32_t ph = (t / STAGES) & 1;
-                mbar_wait(b_full(s), ph);
-                mbar_wait(a_full(s), ph);
+            int it = 0, ti = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+                const int buf = ti & 1;
+                mbar_wait(acc_empty(buf), ((ti >> 1) & 1) ^ 1);        // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t a_hi = a_base + s * STAGE_A, a_lo = a_hi + BM * KSTEP * 2;
-                const uint32_t b_hi = b_base + s * stage_b(BN), b_lo = b_hi + BN * KSTEP * 2;
+                const uint32_t d = tmem_d + (uint32_t)(buf * BN);
+                for (int t = 0; t < p.ksteps; ++t, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(b_full(s), ph);
+                    mbar_wait(a_full(s), ph);
+                    tc_fence_after();
+                    const uint32_t a_hi = a_base + s * STAGE_A, a_lo = a_hi + BM * KSTEP * 2;
+                    const uint32_t b_hi = b_base + s * stage_b(BN), b_lo = b_hi + BN * KSTEP * 2;
 #pragma unroll
-                for (int kq = 0; kq < KSTEP / 16; ++kq) {
-                    const uint64_t dah = kmajor_desc(a_hi + kq * 32), dal = kmajor_desc(a_lo + kq * 32);
-                    const uint64_t dbh = kmajor_desc(b_hi + kq * 32), dbl = kmajor_desc(b_lo + kq * 32);
-                    mma_bf16(tmem_d, dah, dbh, idesc, (t | kq) != 0);
-                    mma_bf16(tmem_d, dal, dbh, idesc, 1);
-                    mma_bf16(tmem_d, dah, dbl, idesc, 1);
+                    for (int kq = 0; kq < KSTEP / 16; ++kq) {
+                        const uint64_t dah = kmajor_desc(a_hi + kq * 32), dal = kmajor_desc(a_lo + kq * 32);
+                        const uint64_t dbh = kmajor_desc(b_hi + kq * 32), dbl = kmajor_desc(b_lo + kq * 32);
+                        mma_bf16(d, dah, dbh, idesc, (t | kq) != 0);
+                        mma_bf16(d, dal, dbh, idesc, 1);
+                        mma_bf16(d, dah, dbl, idesc, 1);
+                    }
+                    mma_commit(a_empty(s));
+                    mma_commit(b_empty(s));
                 }
-                mma_commit(a_empty(s));
-                mma_commit(b_empty(s));
+                mma_commit(acc_full(buf));
             }
-            mma_commit(acc_full);
         }
-    } else {
-        // ================= transform warps (2..9), then epilogue =================
+    } else if (warp < 10) {
+        // ================= transform warps (2..9) =================
         const int tt = threadIdx.x - 64;           // 0..255
         const int r = tt & 127;                    // tile row = pixel
         const int half = tt >> 7;                  // which sub-block of the K step
-        const int px = x0 + r % p.tw, py = y0 + (r / p.tw) % p.th, pb = b0 + r / (p.tw * p.th);
-        const bool row_ok = pb < p.n;              // x,y always inside (tiles divide the image)
         const int sw = r & 7;
-        for (int t = 0; t < p.ksteps; ++t) {
-            const int s = t % STAGES;
-            const uint32_t ph = (t / STAGES) & 1;
-            mbar_wait(f_full(s), ph);
-            const uint32_t src = f32_base + s * STAGE_F32 + half * (BM * SUB * 4) + r * 128;
-            float v[32];
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int x0, y0, b0, n0;
+            tile_coords(tile, x0, y0, b0, n0);
+            const int pb = b0 + r / (p.tw * p.th);
+            const bool row_ok = pb < p.n;
+            for (int t = 0; t < p.ksteps; ++t, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(f_full(s), ph);
+                const uint32_t src = f32_base + s * STAGE_F32 + half * (BM * SUB * 4) + r * 128;
+                float v[32];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float4 q;
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                             : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "r"(src + ((j ^ sw) << 4)));
-                v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(f_empty(s));            // staging tile consumed (values are in registers)
-            if (p.in_scale) {
-                const int sb = 2 * t + half;
-                if (sb < p.subs && row_ok) {
-                    const float* sp = p.in_scale + (long long)pb * p.ci + (sb % p.spb) * SUB;
+                for (int j = 0; j < 8; ++j) {
+                    const float4 q = lds4(src + ((j ^ sw) << 4));
+                    v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(f_empty(s));            // staging tile consumed (values are in registers)
+                if (p.in_scale) {
+                    const int sb = 2 * t + half;
+                    if (sb < p.subs && row_ok) {
+                        const float* sp = p.in_scale + (long long)pb * p.ci + (sb % p.spb) * SUB;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 q = ldg4(sp + 4 * j);
-                        v[4 * j] *= q.x; v[4 * j + 1] *= q.y; v[4 * j + 2] *= q.z; v[4 * j + 3] *= q.w;
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 q = ldg4(sp + 4 * j);
+                            v[4 * j] *= q.x; v[4 * j + 1] *= q.y; v[4 * j + 2] *= q.z; v[4 * j + 3] *= q.w;
+                        }
                     }
                 }
-            }
-            uint32_t hi[16], lo[16];
+                uint32_t hi[16], lo[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
-            mbar_wait(a_empty(s), ph ^ 1);
-            const uint32_t dst_hi = a_base + s * STAGE_A + r * 128, dst_lo = dst_hi + BM * KSTEP * 2;
+                for (int j = 0; j < 16; ++j) split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+                mbar_wait(a_empty(s), ph ^ 1);
+                const uint32_t dst_hi = a_base + s * STAGE_A + r * 128, dst_lo = dst_hi + BM * KSTEP * 2;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint32_t off = (uint32_t)(((4 * half + q) ^ sw) << 4);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst_hi + off), "r"(hi[4 * q]), "r"(hi[4 * q + 1]), "r"(hi[4 * q + 2]), "r"(hi[4 * q + 3]) : "memory");
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst_lo + off), "r"(lo[4 * q]), "r"(lo[4 * q + 1]), "r"(lo[4 * q + 2]), "r"(lo[4 * q + 3]) : "memory");
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t off = (uint32_t)(((4 * half + q) ^ sw) << 4);
+                    sts4(dst_hi + off, hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+                    sts4(dst_lo + off, lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+                }
+                fence_proxy_async();                                // generic-proxy writes -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_full(s));
             }
-            fence_proxy_async();                                // generic-proxy writes -> visible to the tensor core
-            __syncwarp();
-            if (lane == 0) mbar_arrive(a_full(s));
         }
-        // ---------------- epilogue ----------------
-        mbar_wait(acc_full, 0);
-        tc_fence_after();
-        const int q4 = warp & 3;                    // TMEM lane quarter this warp may read
+    } else {
+        // ================= epilogue warps (10..13): one per TMEM lane quarter, a full accumulator row per thread =====
+        const int q4 = warp & 3;
         const int er = q4 * 32 + lane;              // accumulator row = pixel
-        const int chalf = (warp - 2) >> 2;          // which half of the BN columns
-        const int ex = x0 + er % p.tw, ey = y0 + (er / p.tw) % p.th, eb = b0 + er / (p.tw * p.th);
-        const bool e_ok = eb < p.n;
-        const long long pix = ((long long)eb * p.h + ey) * p.w + ex;
-        const float nz = (p.noise && e_ok) ? __ldg(p.noise + pix) : 0.f;
-        float* yrow = p.y + (long long)eb * p.ys[0] + (long long)ey * p.ys[2] + (long long)ex * p.ys[3];
-        constexpr int CW = 16;                                  // columns per tcgen05.ld chunk
-        constexpr int NCH = (BN / 2) / CW;
+        int ti = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+            int x0, y0, b0, n0;
+            tile_coords(tile, x0, y0, b0, n0);
+            const int buf = ti & 1;
+            const int ex = x0 + er % p.tw, ey = y0 + (er / p.tw) % p.th, eb = b0 + er / (p.tw * p.th);
+            const bool e_ok = eb < p.n;
+            const long long pix = ((long long)eb * p.h + ey) * p.w + ex;
+            const float nz = (p.noise && e_ok) ? __ldg(p.noise + pix) : 0.f;
+            float* yrow = p.y + (long long)eb * p.ys[0] + (long long)ey * p.ys[2] + (long long)ex * p.ys[3];
+            mbar_wait(acc_full(buf), (ti >> 1) & 1);
+            tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < NCH; ++c) {
-            const int col0 = chalf * (BN / 2) + c * CW;
-            uint32_t acc[16];
-            tmem_ld16(tmem_d + ((uint32_t)(q4 * 32) << 16) + (uint32_t)col0, acc);
-            if (e_ok) {
-                float u[CW];
-                float umax = 0.f;
+            for (int c = 0; c < BN / 16; ++c) {
+                const int col0 = c * 16;
+                uint32_t acc[16];
+                tmem_ld16(tmem_d + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * BN + col0), acc);
+                if (e_ok) {
 #pragma unroll
-                for (int j = 0; j < CW; ++j) {
-                    const int co = n0 + col0 + j;
-                    float val = __uint_as_float(acc[j]);
-                    if (p.out_scale) val *= __ldg(p.out_scale + (long long)eb * p.co + co);
-                    if (p.bias) val += __ldg(p.bias + co);
-                    val += nz;
-                    u[j] = val;
-                    umax = fmaxf(umax, fabsf(val));
-                }
+                    for (int j = 0; j < 16; j += 4) {
+                        float o[4];
 #pragma unroll
-                for (int j = 0; j < CW; j += 4) {
-                    float o[4];
+                        for (int e = 0; e < 4; ++e) {
+                            const int co = n0 + col0 + j + e;
+                            float val = __uint_as_float(acc[j + e]);
+                            if (p.out_scale) val *= __ldg(p.out_scale + (long long)eb * p.co + co);
+                            if (p.bias) val += __ldg(p.bias + co);
+                            val += nz;
+                            if (p.act == 3) val = val > 0.f ? val : val * p.alpha;
+                            o[e] = val * p.gain;
+                        }
+                        if (p.ys[1] == 1) st4(yrow + n0 + col0 + j, make_float4(o[0], o[1], o[2], o[3]));
+                        else {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float val = u[j + e];
-                        if (p.act == 3) val = val > 0.f ? val : val * p.alpha;
-                        o[e] = val * p.gain;
-                    }
-                    if (p.ys[1] == 1) st4(yrow + n0 + col0 + j, make_float4(o[0], o[1], o[2], o[3]));
-                    else {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) yrow[(long long)(n0 + col0 + j + e) * p.ys[1]] = o[e];
+                            for (int e = 0; e < 4; ++e) yrow[(long long)(n0 + col0 + j + e) * p.ys[1]] = o[e];
+                        }
                     }
                 }
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty(buf));
         }
-        tc_fence_before();
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
@@ -371,7 +389,9 @@ int conv_fwd_tc(const ConvParams& p, cudaStream_t st) {
     const int tiles_b = (p.n + g.tb - 1) / g.tb;
     tp.ksteps = g.ksteps; tp.subs = g.subs; tp.spb = g.spb;
     tp.act = p.act; tp.alpha = p.alpha; tp.gain = p.gain;
-    dim3 grid((unsigned)(tp.tiles_x * tp.tiles_y * tiles_b), (unsigned)(p.co / g.bn));
+    tp.m_tiles = tp.tiles_x * tp.tiles_y * tiles_b;
+    tp.n_tiles = p.co / g.bn;
+    dim3 grid((unsigned)std::min(tp.m_tiles * tp.n_tiles, num_sms()));      // persistent: one CTA per SM
     if (g.bn == 128) return launch_fwd<128>(map, tp, grid, st);
     if (g.bn == 64) return launch_fwd<64>(map, tp, grid, st);
     return launch_fwd<32>(map, tp, grid, st);

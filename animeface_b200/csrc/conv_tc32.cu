@@ -37,7 +37,7 @@ struct Params {
     long long ys[4];
     const unsigned char* wp;
     int n, h, w, ci, co, k;
-    int tw, th, tb, tiles_x, tiles_y;
+    int tw, th, tb, tiles_x, tiles_y, m_tiles, n_tiles;
     int subs, spb;
     int act;
     float alpha, gain;
@@ -61,13 +61,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_fwd_tc32_kernel(const __grid
     const uint32_t tmem_slot = bar_base + 128u;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mt = blockIdx.x;
-    const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tbi = mt / (p.tiles_x * p.tiles_y);
-    const int x0 = tx * p.tw, y0 = ty * p.th, b0 = tbi * p.tb;
-    const int n0 = blockIdx.y * BN;
     const int pad = p.k >> 1;
     constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;          // two accumulator buffers
     const int nseg = (p.subs + SEG - 1) / SEG;
+    // persistent tile loop: tile = n_tile * m_tiles + m_tile
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    auto tile_coords = [&](int tile, int& x0, int& y0, int& b0, int& n0) {
+        const int nt = tile / p.m_tiles, mt = tile % p.m_tiles;
+        x0 = (mt % p.tiles_x) * p.tw;
+        y0 = ((mt / p.tiles_x) % p.tiles_y) * p.th;
+        b0 = (mt / (p.tiles_x * p.tiles_y)) * p.tb;
+        n0 = nt * BN;
+    };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -87,119 +92,137 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_fwd_tc32_kernel(const __grid
         // ================= TMA producer =================
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
-            const unsigned char* wsrc = p.wp + (size_t)blockIdx.y * p.subs * (2 * tile_b(BN));
-            for (int t = 0; t < p.subs; ++t) {
-                const int s = t % STAGES;
-                const uint32_t ph = (t / STAGES) & 1;
-                mbar_wait(empty(s), ph ^ 1);
-                mbar_expect_tx(b_full(s), 2 * tile_b(BN));
-                bulk_load(st_b_big(s), wsrc + (size_t)t * (2 * tile_b(BN)), 2 * tile_b(BN), b_full(s));
-                const int tap = t / p.spb, c0 = (t % p.spb) * SUB;
-                const int dy = tap / p.k - pad, dx = tap % p.k - pad;
-                mbar_expect_tx(f_full(s), TILE_A);
-                tma_load_4d(st_a_big(s), &xmap, f_full(s), c0, x0 + dx, y0 + dy, b0);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int x0, y0, b0, n0;
+                tile_coords(tile, x0, y0, b0, n0);
+                const unsigned char* wsrc = p.wp + (size_t)(n0 / BN) * p.subs * (2 * tile_b(BN));
+                for (int t = 0; t < p.subs; ++t, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(empty(s), ph ^ 1);
+                    mbar_expect_tx(b_full(s), 2 * tile_b(BN));
+                    bulk_load(st_b_big(s), wsrc + (size_t)t * (2 * tile_b(BN)), 2 * tile_b(BN), b_full(s));
+                    const int tap = t / p.spb, c0 = (t % p.spb) * SUB;
+                    const int dy = tap / p.k - pad, dx = tap % p.k - pad;
+                    mbar_expect_tx(f_full(s), TILE_A);
+                    tma_load_4d(st_a_big(s), &xmap, f_full(s), c0, x0 + dx, y0 + dy, b0);
+                }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
             constexpr uint32_t idesc = idesc_tf32(BM, BN);
-            for (int t = 0; t < p.subs; ++t) {
-                const int s = t % STAGES;
-                const uint32_t ph = (t / STAGES) & 1;
-                const int seg = t / SEG, buf = seg & 1;
-                const bool seg_start = (t % SEG) == 0;
-                if (seg_start) mbar_wait(acc_empty(buf), ((seg >> 1) & 1) ^ 1);
-                mbar_wait(b_full(s), ph);
-                mbar_wait(a_full(s), ph);
-                tc_fence_after();
-                const uint32_t d = tmem_d + (uint32_t)(buf * BN);
+            int it = 0, sg = 0;                      // global stage / segment counters (continue across tiles)
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                for (int t = 0; t < p.subs; ++t, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    const int buf = sg & 1;
+                    const bool seg_start = (t % SEG) == 0;
+                    if (seg_start) { mbar_wait(acc_empty(buf), ((sg >> 1) & 1) ^ 1); tc_fence_after(); }
+                    mbar_wait(b_full(s), ph);
+                    mbar_wait(a_full(s), ph);
+                    tc_fence_after();
+                    const uint32_t d = tmem_d + (uint32_t)(buf * BN);
 #pragma unroll
-                for (int kq = 0; kq < SUB / 8; ++kq) {
-                    const uint64_t dab = kmajor_desc(st_a_big(s) + kq * 32), das = kmajor_desc(st_a_small(s) + kq * 32);
-                    const uint64_t dbb = kmajor_desc(st_b_big(s) + kq * 32), dbs = kmajor_desc(st_b_small(s) + kq * 32);
-                    mma_tf32(d, dab, dbb, idesc, !(seg_start && kq == 0));
-                    mma_tf32(d, das, dbb, idesc, 1);
-                    mma_tf32(d, dab, dbs, idesc, 1);
+                    for (int kq = 0; kq < SUB / 8; ++kq) {
+                        const uint64_t dab = kmajor_desc(st_a_big(s) + kq * 32), das = kmajor_desc(st_a_small(s) + kq * 32);
+                        const uint64_t dbb = kmajor_desc(st_b_big(s) + kq * 32), dbs = kmajor_desc(st_b_small(s) + kq * 32);
+                        mma_tf32(d, dab, dbb, idesc, !(seg_start && kq == 0));
+                        mma_tf32(d, das, dbb, idesc, 1);
+                        mma_tf32(d, dab, dbs, idesc, 1);
+                    }
+                    mma_commit(empty(s));
+                    if ((t % SEG) == SEG - 1 || t == p.subs - 1) { mma_commit(acc_full(buf)); ++sg; }
                 }
-                mma_commit(empty(s));
-                if ((t % SEG) == SEG - 1 || t == p.subs - 1) mma_commit(acc_full(buf));
             }
         }
     } else if (warp < 10) {
         // ================= transform: 2 threads per pixel row, 4 x 16 B chunks (16 channels) each =================
         const int tt = threadIdx.x - 64;
         const int r = tt & 127, half = tt >> 7;
-        const int pb = b0 + r / (p.tw * p.th);
-        const bool row_ok = pb < p.n;
         const int sw = r & 7;
-        for (int t = 0; t < p.subs; ++t) {
-            const int s = t % STAGES;
-            const uint32_t ph = (t / STAGES) & 1;
-            mbar_wait(f_full(s), ph);
-            const uint32_t row_big = st_a_big(s) + r * 128, row_small = st_a_small(s) + r * 128;
-            const float* sp = (p.in_scale && row_ok) ? p.in_scale + (long long)pb * p.ci + (t % p.spb) * SUB + 16 * half : nullptr;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int x0, y0, b0, n0;
+            tile_coords(tile, x0, y0, b0, n0);
+            const int pb = b0 + r / (p.tw * p.th);
+            const bool row_ok = pb < p.n;
+            for (int t = 0; t < p.subs; ++t, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(f_full(s), ph);
+                const uint32_t row_big = st_a_big(s) + r * 128, row_small = st_a_small(s) + r * 128;
+                const float* sp = (p.in_scale && row_ok) ? p.in_scale + (long long)pb * p.ci + (t % p.spb) * SUB + 16 * half : nullptr;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint32_t off = (uint32_t)(((4 * half + q) ^ sw) << 4);
-                float4 v = lds4(row_big + off);
-                if (sp) v = mul4(v, ldg4(sp + 4 * q));
-                const uint32_t g0 = rna_tf32(v.x), g1 = rna_tf32(v.y), g2 = rna_tf32(v.z), g3 = rna_tf32(v.w);
-                sts4(row_big + off, g0, g1, g2, g3);
-                sts4(row_small + off, rna_tf32(v.x - __uint_as_float(g0)), rna_tf32(v.y - __uint_as_float(g1)),
-                     rna_tf32(v.z - __uint_as_float(g2)), rna_tf32(v.w - __uint_as_float(g3)));
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t off = (uint32_t)(((4 * half + q) ^ sw) << 4);
+                    float4 v = lds4(row_big + off);
+                    if (sp) v = mul4(v, ldg4(sp + 4 * q));
+                    const uint32_t g0 = rna_tf32(v.x), g1 = rna_tf32(v.y), g2 = rna_tf32(v.z), g3 = rna_tf32(v.w);
+                    sts4(row_big + off, g0, g1, g2, g3);
+                    sts4(row_small + off, rna_tf32(v.x - __uint_as_float(g0)), rna_tf32(v.y - __uint_as_float(g1)),
+                         rna_tf32(v.z - __uint_as_float(g2)), rna_tf32(v.w - __uint_as_float(g3)));
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_full(s));
             }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(a_full(s));
         }
     } else {
         // ================= promotion (fp32 RN adds of the segment sums) + epilogue =================
         const int q4 = warp & 3;                    // TMEM lane quarter this warp may read
         const int chalf = (warp - 10) >> 2;         // which half of the BN columns
         constexpr int HALF = BN / 2;
-        float racc[HALF];
-#pragma unroll
-        for (int j = 0; j < HALF; ++j) racc[j] = 0.f;
-        for (int seg = 0; seg < nseg; ++seg) {
-            const int buf = seg & 1;
-            mbar_wait(acc_full(buf), (seg >> 1) & 1);
-            tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < HALF / 16; ++c) {
-                uint32_t v[16];
-                tmem_ld16(tmem_d + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * BN + chalf * HALF + c * 16), v);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) racc[c * 16 + j] += __uint_as_float(v[j]);
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty(buf));
-        }
         const int er = q4 * 32 + lane;
-        const int ex = x0 + er % p.tw, ey = y0 + (er / p.tw) % p.th, eb = b0 + er / (p.tw * p.th);
-        if (eb < p.n) {
-            const long long pix = ((long long)eb * p.h + ey) * p.w + ex;
-            const float nz = p.noise ? __ldg(p.noise + pix) : 0.f;
-            float* yrow = p.y + (long long)eb * p.ys[0] + (long long)ey * p.ys[2] + (long long)ex * p.ys[3];
+        int sg = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int x0, y0, b0, n0;
+            tile_coords(tile, x0, y0, b0, n0);
+            float racc[HALF];
 #pragma unroll
-            for (int j = 0; j < HALF; j += 4) {
-                float o[4];
+            for (int j = 0; j < HALF; ++j) racc[j] = 0.f;
+            for (int seg = 0; seg < nseg; ++seg, ++sg) {
+                const int buf = sg & 1;
+                mbar_wait(acc_full(buf), (sg >> 1) & 1);
+                tc_fence_after();
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int co = n0 + chalf * HALF + j + e;
-                    float val = racc[j + e];
-                    if (p.out_scale) val *= __ldg(p.out_scale + (long long)eb * p.co + co);
-                    if (p.bias) val += __ldg(p.bias + co);
-                    val += nz;
-                    if (p.act == 3) val = val > 0.f ? val : val * p.alpha;
-                    o[e] = val * p.gain;
+                for (int c = 0; c < HALF / 16; ++c) {
+                    uint32_t v[16];
+                    tmem_ld16(tmem_d + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * BN + chalf * HALF + c * 16), v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) racc[c * 16 + j] += __uint_as_float(v[j]);
                 }
-                const int cbase = n0 + chalf * HALF + j;
-                if (p.ys[1] == 1) st4(yrow + cbase, make_float4(o[0], o[1], o[2], o[3]));
-                else {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty(buf));
+            }
+            const int ex = x0 + er % p.tw, ey = y0 + (er / p.tw) % p.th, eb = b0 + er / (p.tw * p.th);
+            if (eb < p.n) {
+                const long long pix = ((long long)eb * p.h + ey) * p.w + ex;
+                const float nz = p.noise ? __ldg(p.noise + pix) : 0.f;
+                float* yrow = p.y + (long long)eb * p.ys[0] + (long long)ey * p.ys[2] + (long long)ex * p.ys[3];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) yrow[(long long)(cbase + e) * p.ys[1]] = o[e];
+                for (int j = 0; j < HALF; j += 4) {
+                    float o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int co = n0 + chalf * HALF + j + e;
+                        float val = racc[j + e];
+                        if (p.out_scale) val *= __ldg(p.out_scale + (long long)eb * p.co + co);
+                        if (p.bias) val += __ldg(p.bias + co);
+                        val += nz;
+                        if (p.act == 3) val = val > 0.f ? val : val * p.alpha;
+                        o[e] = val * p.gain;
+                    }
+                    const int cbase = n0 + chalf * HALF + j;
+                    if (p.ys[1] == 1) st4(yrow + cbase, make_float4(o[0], o[1], o[2], o[3]));
+                    else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) yrow[(long long)(cbase + e) * p.ys[1]] = o[e];
+                    }
                 }
             }
         }
@@ -292,7 +315,9 @@ int conv_fwd_tc32(const ConvParams& p, cudaStream_t st) {
     const int tiles_b = (p.n + g.tb - 1) / g.tb;
     tp.subs = g.subs; tp.spb = g.spb;
     tp.act = p.act; tp.alpha = p.alpha; tp.gain = p.gain;
-    dim3 grid((unsigned)(tp.tiles_x * tp.tiles_y * tiles_b), (unsigned)(p.co / g.bn));
+    tp.m_tiles = tp.tiles_x * tp.tiles_y * tiles_b;
+    tp.n_tiles = p.co / g.bn;
+    dim3 grid((unsigned)std::min(tp.m_tiles * tp.n_tiles, num_sms()));      // persistent: one CTA per SM
     if (g.bn == 128) return tc32::launch<128>(map, tp, grid, st);
     if (g.bn == 64) return tc32::launch<64>(map, tp, grid, st);
     return tc32::launch<32>(map, tp, grid, st);

@@ -17,7 +17,7 @@ import torch
 
 from .. import _lib
 
-IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC32 = 0, 1, 2, 3
+IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC32, IMPL_HALO, IMPL_HALO32 = 0, 1, 2, 3, 4, 5
 _default_impl = IMPL_AUTO
 
 # bench.py sets this to a list to time every convolution launch with CUDA events on the launching stream:
@@ -42,10 +42,11 @@ class _timed:
 
 
 def set_default_impl(impl: int) -> None:
-    """0 = auto (tcgen05 where the shape allows -- fp32-class tf32x3 for forward convs, bf16x3 for gradients --
-    else fp32 SIMT), 1 = SIMT everywhere, 2 = prefer bf16x3 for every conv, 3 = prefer tf32x3 for every conv."""
+    """0 = auto (tcgen05 where the shape allows -- fp32-class tf32x3 for forward convs, bf16x3 for gradients; halo
+    kernels where the image tiles by 8x16 -- else fp32 SIMT), 1 = SIMT everywhere, 2..5 = prefer that tcgen05 kernel
+    (per-tap bf16x3 / per-tap tf32x3 / halo bf16x3 / halo tf32x3) wherever it applies."""
     global _default_impl
-    assert impl in (0, 1, 2, 3)
+    assert impl in (0, 1, 2, 3, 4, 5)
     _default_impl = impl
 
 

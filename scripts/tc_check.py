@@ -15,7 +15,7 @@ def err(a, b):
     return float((a - b).abs().max() / b.abs().max())
 
 
-cases = [(8, 32, 64, 3, 16), (8, 64, 64, 3, 32), (3, 64, 128, 3, 8), (8, 128, 128, 1, 16), (2, 32, 32, 3, 64),
+cases = [(2, 64, 64, 3, 16), (8, 32, 64, 3, 16), (8, 64, 64, 3, 32), (3, 64, 128, 3, 8), (8, 128, 128, 1, 16), (2, 32, 32, 3, 64),
          (8, 512, 512, 3, 4), (2, 64, 32, 3, 128), (1, 256, 256, 3, 16), (4, 64, 64, 1, 256), (5, 96, 160, 3, 8)]
 which = sys.argv[1] if len(sys.argv) > 1 else 'all'
 for idx, (n, ci, co, k, hw) in enumerate(cases):
@@ -35,7 +35,7 @@ for idx, (n, ci, co, k, hw) in enumerate(cases):
         ref1 = F.leaky_relu(F.conv2d(x * s[:, :, None, None], w * coef, padding=k // 2) * d[:, :, None, None] + b[None, :, None, None] + nz, 0.2)
         ref64 = F.leaky_relu(F.conv2d((x * s[:, :, None, None]).double(), (w * coef).double(), padding=k // 2) * d[:, :, None, None].double() + b[None, :, None, None].double() + nz.double(), 0.2)
         e32 = float((ref1.double() - ref64).abs().max() / ref64.abs().max())
-        for impl in (2, 3):
+        for impl in ((2, 3, 4, 5) if hw % 16 == 0 else (2, 3)):
             y0 = C._conv_raw(x, w, coef, False, impl=impl)
             y1 = C._conv_raw(x, w, coef, False, in_scale=s, out_scale=d, bias=b, noise=nz, slope=0.2, impl=impl)
             e64 = float((y1.double() - ref64).abs().max() / ref64.abs().max())
@@ -44,6 +44,8 @@ for idx, (n, ci, co, k, hw) in enumerate(cases):
         if ci in (32, 64) or ci % 128 == 0:
             ref2 = F.conv_transpose2d(gy, w * coef, padding=k // 2)
             out.append(f'dgrad {err(C._conv_raw(gy, w, coef, True, impl=2), ref2):.1e}')
+            if hw % 16 == 0:
+                out.append(f'dgrad-halo {err(C._conv_raw(gy, w, coef, True, impl=4), ref2):.1e}')
     if which in ('all', 'wgrad'):
         xr = x.detach().clone().requires_grad_(False)
         wr = w.detach().clone().requires_grad_(True)
