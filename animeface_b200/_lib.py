@@ -46,6 +46,8 @@ SIGNATURES = {
     'sg2_scale_reduce_hw': (_int, [_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _vp]),
     'sg2_modconv_bwd_prep': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _f, _vp]),
     'sg2_ema_update': (_int, [_vp, _vp, _i64, _f, _vp]),
+    'sg2_counter_add': (_int, [_vp, _int, _int, _int, _int, _vp]),
+    'sg2_adam_multi': (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _int, _f, _f, _f, _f, _f, _vp]),
     'sg2_adam_ema': (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _f, _f, _vp]),
 }
 

@@ -7,7 +7,8 @@ nnutils/training.py:23-40 become one kernel in ``update_ema``).
   * parameters are re-pointed to views of ONE flat buffer; m / v are flat too;
   * ``step()`` packs the gradients with one multi-tensor copy, all-reduces the flat buffer ONCE when
     torch.distributed is initialised (the only collective of the data-parallel step; there is no DDP in the
-    reference, nnutils/accelerate.py:8-11), and launches ``sg2_adam_ema`` per run of tensors;
+    reference, nnutils/accelerate.py:8-11), and launches ``sg2_adam_multi`` once over the whole buffer (per-tensor
+    step counts live on the device, so the call replays unchanged inside a CUDA graph);
   * tensors whose grad is None are skipped exactly like torch.optim.Adam skips them (their step count does
     not advance) -- the 12 ``InjectNoise.scale`` and, on R1 steps, the last bias of D.
 """
@@ -42,12 +43,13 @@ class FlatAdam(torch.optim.Optimizer):
         self._M = torch.zeros_like(self._P)
         self._V = torch.zeros_like(self._P)
         self._steps = torch.zeros(len(ps), dtype=torch.int64, device=dev)
-        self._host_steps = [0] * len(ps)
+        self._present = torch.zeros(len(ps), dtype=torch.int32, device=dev)
+        self._coef = torch.zeros(2 * len(ps), dtype=torch.float32, device=dev)
         for p, o, n in zip(ps, self._offs, self._sizes):
             self._P[o:o + n].copy_(p.data.reshape(-1))
             p.data = self._P[o:o + n].view(p.shape)
+        self._seg_off = torch.tensor(self._offs + [self._total], dtype=torch.int64, device=dev)
         self._gviews = [self._G[o:o + n].view(p.shape) for p, o, n in zip(ps, self._offs, self._sizes)]
-        self._idx_cache = {}
         if model is not None:
             model._sg2_flat = self._P
         if ema_model is not None:
@@ -92,28 +94,18 @@ class FlatAdam(torch.optim.Optimizer):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self._G)                      # the one collective of the step
             scale = 1.0 / dist.get_world_size()
-        key = tuple(present)
-        if key not in self._idx_cache:
-            self._idx_cache[key] = torch.tensor(present, dtype=torch.int64, device=self._P.device)
-        self._steps.index_add_(0, self._idx_cache[key], torch.ones_like(self._idx_cache[key]))
-        for i in present:
-            self._host_steps[i] += 1
         lib = _lib.load()
         st = _lib.stream_ptr(self._P)
-        # maximal runs of consecutive present tensors sharing a step count -> one launch each
-        run = [present[0]]
-        runs = []
-        for i in present[1:]:
-            if i == run[-1] + 1 and self._host_steps[i] == self._host_steps[run[0]]:
-                run.append(i)
-            else:
-                runs.append(run)
-                run = [i]
-        runs.append(run)
-        for r in runs:
-            o0 = self._offs[r[0]]
-            o1 = self._offs[r[-1]] + self._sizes[r[-1]]
-            _lib.check(lib.sg2_adam_ema(
-                self._P.data_ptr() + 4 * o0, self._G.data_ptr() + 4 * o0, self._M.data_ptr() + 4 * o0,
-                self._V.data_ptr() + 4 * o0, None, o1 - o0, self._steps.data_ptr() + 8 * r[0],
-                float(lr), float(b1), float(b2), float(eps), float(scale), 0.0, st), 'sg2_adam_ema')
+        # presence flags from plain integer ranges (no host->device copy: the call replays inside a CUDA graph)
+        self._present.zero_()
+        run = [present[0], present[0]]
+        for i in present[1:] + [None]:
+            if i is not None and i == run[1] + 1:
+                run[1] = i
+                continue
+            _lib.check(lib.sg2_counter_add(self._present.data_ptr(), run[0], run[1] - run[0] + 1, 1, 0, st), 'sg2_counter_add')
+            run = [i, i]
+        _lib.check(lib.sg2_adam_multi(
+            self._P.data_ptr(), self._G.data_ptr(), self._M.data_ptr(), self._V.data_ptr(), self._total,
+            self._seg_off.data_ptr(), self._steps.data_ptr(), self._present.data_ptr(), self._coef.data_ptr(), len(self._ps),
+            float(lr), float(b1), float(b2), float(eps), float(scale), st), 'sg2_adam_multi')

@@ -97,15 +97,16 @@ class Trainer:
         it = self.batches_done if it is None else it
         return it % self.cfg.d_k == 0 and self.cfg.r1_lambda > 0 and it != 0
 
-    def step(self, real: torch.Tensor):
-        """real: [B,3,H,W] on the device.  Returns (D_loss, G_loss, fake) device tensors; no host sync."""
+    def step(self, real: torch.Tensor, force_r1=None):
+        """real: [B,3,H,W] on the device.  Returns (D_loss, G_loss, fake) device tensors; no host sync.
+        force_r1 overrides the lazy-regularisation schedule for this call (used to warm up / capture graphs)."""
         cfg, G, D = self.cfg, self.G, self.D
         B, dev = real.size(0), real.device
         self.opt_g.zero_grad()
         self.opt_d.zero_grad()
         # ---- discriminator phase (utils.py:60-86)
         z = rng.randn(B, cfg.style_dim, device=dev)
-        r1_step = self.is_r1_step()
+        r1_step = self.is_r1_step() if force_r1 is None else bool(force_r1)
         real_aug = self.augment(real)
         with torch.no_grad():
             fake, _ = G(z)
@@ -134,6 +135,55 @@ class Trainer:
         update_ema(G, self.G_ema, cfg.ema_decay)
         self.batches_done += 1
         return D_loss.detach(), G_loss.detach(), fake.detach()
+
+
+class GraphedTrainer:
+    """``Trainer.step`` captured into CUDA graphs -- one for the normal step, one for the lazy-R1 step -- and replayed.
+
+    A step launches ~1300 kernels (convolutions, resampling, elementwise, optimizer); replaying a graph removes the
+    Python / launch gaps between them (guide rule: "capture launch-bound inner loops in CUDA graphs").  Everything in
+    the step is capture-safe: no host syncs, random draws from the device generator, tensor maps and kernel arguments
+    are functions of addresses that the graph's private memory pool keeps fixed, the Adam step counters live on the
+    device.  Policy: the first step of each kind runs eagerly (it also warms kernels up), the second one is captured
+    and replayed, later ones are replays.  ``prime()`` does that up front for both kinds."""
+
+    def __init__(self, trainer: Trainer):
+        self.t = trainer
+        self.static_real = None
+        self.graphs = {}          # kind (is_r1) -> (CUDAGraph, outputs)
+        self.seen = set()
+
+    def prime(self, real):
+        """Eager + capture for both kinds now (4 extra optimizer steps; two of them are out-of-schedule R1 steps)."""
+        for kind in (False, True):
+            self.step(real, force_r1=kind)
+            self.step(real, force_r1=kind)
+
+    def step(self, real, force_r1=None):
+        t = self.t
+        kind = t.is_r1_step() if force_r1 is None else bool(force_r1)
+        if self.static_real is None:
+            self.static_real = real.clone()
+        if kind in self.graphs:
+            self.static_real.copy_(real)
+            g, out = self.graphs[kind]
+            g.replay()
+            t.batches_done += 1
+            return out
+        if kind not in self.seen:
+            self.seen.add(kind)
+            return t.step(real, force_r1=kind)
+        self.static_real.copy_(real)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        done = t.batches_done
+        with torch.cuda.graph(g):
+            out = t.step(self.static_real, force_r1=kind)
+        t.batches_done = done               # capture does not execute: the replay below is the real step
+        self.graphs[kind] = (g, out)
+        g.replay()
+        t.batches_done += 1
+        return out
 
 
 def train(max_iter, dataset, cfg: TrainConfig, device, log_every=100, log=print):

@@ -195,6 +195,17 @@ int sg2_adam_ema(float* p, const float* g, float* m, float* v, float* ema,
                  int64_t numel, const int64_t* step, float lr, float beta1, float beta2,
                  float eps, float grad_scale, float ema_decay, sg2_stream_t stream);
 int sg2_ema_update(float* ema, const float* p, int64_t numel, float decay, sg2_stream_t stream);
+/* Multi-tensor form: ONE launch over the flat buffer with exact per-tensor step counts.
+ * seg_off: int64[nseg+1] element offsets of the tensors inside the flat buffer (16-byte aligned segments);
+ * steps: int64[nseg] per-tensor step counts (device; incremented here for present tensors);
+ * present: int32[nseg], 0 = the tensor had no gradient this step -> skipped exactly like torch.optim.Adam skips
+ * grad=None (its moments and step count do not move); coef_ws: float2[nseg] workspace.                        */
+int sg2_adam_multi(float* p, const float* g, float* m, float* v, int64_t numel, const int64_t* seg_off,
+                   int64_t* steps, const int* present, void* coef_ws, int nseg,
+                   float lr, float beta1, float beta2, float eps, float grad_scale, sg2_stream_t stream);
+/* counters[first .. first+count) += delta  (the per-tensor Adam step counts; a kernel so that it is captured
+ * in CUDA graphs without any host->device copy). */
+int sg2_counter_add(void* counters, int first, int count, int delta, int is64, sg2_stream_t stream);
 
 #ifdef __cplusplus
 }

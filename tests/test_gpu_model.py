@@ -128,3 +128,27 @@ def test_full_size_step_runs_and_is_finite():
     assert _lib.launch_count() - before > 300
     assert not torch.equal(p0, opt_g.flat_params)
     assert float((G_ema._sg2_flat - p0).abs().max()) > 0
+
+
+def test_cuda_graph_trainer_matches_schedule_and_trains():
+    """GraphedTrainer: eager -> capture -> replay for both step kinds; the replayed steps keep training (losses finite,
+    parameters move, Adam step counters advance once per step for tensors that have a gradient)."""
+    from animeface_b200.train import GraphedTrainer, TrainConfig, Trainer, build_models, build_optimizers
+    torch.manual_seed(0)
+    cfg = TrainConfig(image_size=32, style_dim=64, channels=8, max_channels=64, map_num_layers=2, batch_size=8, d_k=3)
+    G, G_ema, D = build_models(cfg, DEV)
+    opt_g, opt_d = build_optimizers(cfg, G, G_ema, D)
+    gt = GraphedTrainer(Trainer(cfg, G, G_ema, D, opt_g, opt_d))
+    kinds, snaps = [], []
+    for it in range(10):
+        kinds.append(gt.t.is_r1_step())
+        d_loss, g_loss, fake = gt.step(torch.rand(8, 3, 32, 32, device=DEV) * 2 - 1)
+        assert torch.isfinite(d_loss) and torch.isfinite(g_loss) and torch.isfinite(fake).all(), it
+        snaps.append(opt_d.flat_params.clone())
+    assert kinds == [False, False, False, True, False, False, True, False, False, True]
+    assert set(gt.graphs) == {False, True}                      # both kinds were captured (2nd occurrence) ...
+    assert gt.t.batches_done == 10
+    for a, b in zip(snaps[:-1], snaps[1:]):
+        assert not torch.equal(a, b)                            # ... and every replay really stepped the optimizer
+    steps = opt_d._steps.cpu()
+    assert int(steps.max()) == 10 and int(steps.min()) >= 7     # tensors without a gradient on the 3 R1 steps lag by 3

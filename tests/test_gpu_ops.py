@@ -16,7 +16,7 @@ def T(a, grad=False):
 
 
 def N(t):
-    return t.detach().float().cpu().numpy()
+    return t.detach().double().cpu().numpy()
 
 
 # ------------------------------------------------------------------------------------------ upfirdn2d
@@ -272,3 +272,49 @@ def test_flat_adam_matches_torch_adam_and_skips_none_grads():
         assert rel_err(N(pb), N(pa)) < 1e-5
     for pa, pb in zip(ema_a.parameters(), ema_b.parameters()):
         assert rel_err(N(pb), N(pa)) < 1e-5
+
+
+# ------------------------------------------------------------------------- tcgen05 kernels, every variant
+@pytest.mark.parametrize('impl,tol', [(2, 5e-5), (3, 3e-6), (4, 5e-5), (5, 3e-6)])
+@pytest.mark.parametrize('n,ci,co,k,hw', [(2, 64, 64, 3, 16), (8, 32, 64, 3, 16), (3, 64, 128, 3, 32), (4, 128, 32, 1, 16), (1, 256, 256, 3, 16)])
+def test_tcgen05_conv_variants_vs_fp64(impl, tol, n, ci, co, k, hw):
+    """impl 2/4 = bf16x3 (per-tap / halo), 3/5 = tf32x3 + promotion (fp32-class): plain, fused epilogue, data gradient."""
+    from animeface_b200.ops import conv2d as C
+    import torch.nn.functional as F
+    g = torch.Generator(device=DEV).manual_seed(impl * 100 + ci)
+    x = torch.randn(n, ci, hw, hw, device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    w = torch.randn(co, ci, k, k, device=DEV, generator=g)
+    s = torch.randn(n, ci, device=DEV, generator=g)
+    d = torch.rand(n, co, device=DEV, generator=g) + 0.5
+    b = torch.randn(co, device=DEV, generator=g)
+    nz = torch.randn(n, 1, hw, hw, device=DEV, generator=g)
+    gy = torch.randn(n, co, hw, hw, device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    coef = 0.05
+    ref = F.leaky_relu(F.conv2d((x * s[:, :, None, None]).double(), (w * coef).double(), padding=k // 2) * d[:, :, None, None].double()
+                       + b[None, :, None, None].double() + nz.double(), 0.2)
+    y = C._conv_raw(x, w, coef, False, in_scale=s, out_scale=d, bias=b, noise=nz, slope=0.2, impl=impl)
+    assert rel_err(N(y), N(ref)) < tol
+    y_nchw = C._conv_raw(x, w, coef, False, in_scale=s, out_scale=d, bias=b, noise=nz, slope=0.2, impl=impl, out_nchw=True)
+    assert y_nchw.is_contiguous() and torch.equal(y_nchw, y.contiguous())
+    ref_t = F.conv_transpose2d(gy.double(), (w * coef).double(), padding=k // 2)
+    gx = C._conv_raw(gy, w, coef, True, impl=impl)
+    assert rel_err(N(gx), N(ref_t)) < tol
+
+
+@pytest.mark.parametrize('n,ci,co,k,hw', [(8, 32, 64, 3, 16), (2, 64, 32, 3, 64), (8, 128, 128, 1, 16), (5, 96, 160, 3, 8), (8, 512, 512, 3, 4)])
+def test_tcgen05_wgrad_vs_fp64(n, ci, co, k, hw):
+    from animeface_b200.ops import conv2d as C
+    import torch.nn.functional as F
+    g = torch.Generator(device=DEV).manual_seed(ci + co)
+    x = torch.randn(n, ci, hw, hw, device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    gy = torch.randn(n, co, hw, hw, device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    s = torch.randn(n, ci, device=DEV, generator=g)
+    d = torch.rand(n, co, device=DEV, generator=g) + 0.5
+    w = torch.zeros(co, ci, k, k, device=DEV, dtype=torch.float64, requires_grad=True)
+    coef = 0.07
+    yr = F.conv2d((x * s[:, :, None, None]).double(), w * coef, padding=k // 2) * d[:, :, None, None].double()
+    ref, = torch.autograd.grad(yr, w, gy.double())
+    dw = C._wgrad_raw(x, gy, k, coef, in_scale=s, out_scale=d, impl=2)
+    assert rel_err(N(dw), N(ref)) < 5e-5
+    dw1 = C._wgrad_raw(x, gy, k, coef, in_scale=s, out_scale=d, impl=1)
+    assert rel_err(N(dw1), N(ref)) < 5e-6
