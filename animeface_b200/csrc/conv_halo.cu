@@ -11,8 +11,11 @@
 //            (an 8-pixel tile row is an 8-row core-matrix group, consecutive tile rows are PW patch rows apart), so
 //            all taps read the same converted patch; B = pre-packed weight tile of (tap, channel block), SWIZZLE_128B.
 // PRECISE = false: bf16x3 (hi/lo planes, kind::f16, 64 channels per block)           -> data gradients
-// PRECISE = true : tf32x3 + promotion (big/small planes, kind::tf32, 32 channels per block, TMEM accumulator promoted to
-//                  fp32 registers every 2 taps = 8 big*big MMAs)                      -> forward convs, fp32-class
+// PRECISE = true : fp16x3 + promotion: big = rn_f16(v), small = rn_f16((v - big) * 2^11) (22 mantissa bits together, like
+//                  the tf32 pair of conv_tc32.cu but at the fp16 MMA rate); D1 += big*big and D2 += small*big + big*small
+//                  in separate TMEM accumulators, promoted to fp32 registers (acc += D1 + 2^-11 D2) every 2 taps
+//                  = 8 chained big*big MMAs                                             -> forward convs, fp32-class
+//                  (fp16 range: operands saturate at +-65504; forward activations and weights of this path are O(1))
 // Persistent CTAs (one per SM), double-buffered planes and TMEM accumulators, dedicated epilogue warps.
 // Warp roles: 0 patch TMA, 1 MMA (+TMEM alloc), 2..9 transform, 10.. epilogue/promotion, last = weight TMA.
 #include "tc_common.cuh"
@@ -35,12 +38,13 @@ template <int BN, bool PRECISE> struct Cfg {
     static constexpr int NWARPS = 10 + EPI_WARPS + 1;
     static constexpr int NTHREADS = NWARPS * 32;
     static constexpr int BWARP = NWARPS - 1;                       // weight producer warp
-    static constexpr int KB = PRECISE ? 32 : 64;                   // input channels per block (128 B of K per operand row)
-    static constexpr int BOXES = PRECISE ? 1 : 2;                  // TMA boxes (32 ch) per block
+    static constexpr int KB = 64;                                  // input channels per block (128 B of K per operand row)
+    static constexpr int BOXES = 2;                                // TMA boxes (32 ch) per block
     static constexpr int SLOTS = BN == 128 ? 1 : 2;                // staging slots (boxes in flight); 1 keeps BN=128 under 227 KB
     static constexpr int BTILE = 2 * BN * 128;                     // two planes of [BN rows x 128 B]
     static constexpr int SMEM = 1024 + SLOTS * SLOT_BYTES + 2 * 2 * PLANE_PITCH + BSTAGES * BTILE + 256;
-    static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+    static constexpr int ACC_COLS = PRECISE ? 2 * BN : BN;         // one accumulator buffer (PRECISE: D1 | D2)
+    static constexpr uint32_t TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
 };
 
 struct Params {
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            constexpr uint32_t idesc = PRECISE ? idesc_tf32(BM, BN) : idesc_bf16(BM, BN);
+            constexpr uint32_t idesc = PRECISE ? idesc_f16(BM, BN) : idesc_bf16(BM, BN);
             int bt = 0, kbg = 0, sg = 0;                  // global weight-tile / channel-block / accumulator-segment counters
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 int f = 0;                                // flat (kb, tap) index inside the tile
@@ -160,7 +164,7 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
                         const int s = bt % BSTAGES;
                         mbar_wait(b_full(s), (bt / BSTAGES) & 1);
                         tc_fence_after();
-                        const uint32_t d = tmem_d + (uint32_t)(abuf * BN);
+                        const uint32_t d = tmem_d + (uint32_t)(abuf * C::ACC_COLS);
                         const int dy = t / p.k, dx = t % p.k;                      // already offset by +pad
                         const uint32_t arow = (uint32_t)(dy * PW + dx) * 16u;
                         const uint32_t a0 = plane(pbuf, 0) + arow, a1 = plane(pbuf, 1) + arow;
@@ -171,7 +175,9 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
                             const uint64_t db0 = kmajor_desc(b0_ + kq * 32), db1 = kmajor_desc(b1_ + kq * 32);
                             const uint32_t accum = !(seg_start && kq == 0);
                             if (PRECISE) {
-                                mma_tf32(d, da0, db0, idesc, accum); mma_tf32(d, da1, db0, idesc, 1); mma_tf32(d, da0, db1, idesc, 1);
+                                mma_bf16(d, da0, db0, idesc, accum);                      // D1 += big * big
+                                mma_bf16(d + BN, da1, db0, idesc, accum);                 // D2 += small * big
+                                mma_bf16(d + BN, da0, db1, idesc, 1);                     //     + big * small
                             } else {
                                 mma_bf16(d, da0, db0, idesc, accum); mma_bf16(d, da1, db0, idesc, 1); mma_bf16(d, da0, db1, idesc, 1);
                             }
@@ -222,28 +228,18 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
                                 }
                             }
                         }
-                        if (PRECISE) {
-                            // 16 channels = 4 chunks of 4 tf32; chunk index within the 32-channel block = 4*half + q
-                            uint32_t g[16], sm[16];
+                        // 16 channels = 2 chunks of 8 halves; chunk index within the 64-channel block = 4*hb + 2*half + q
+                        uint32_t hi[8], lo[8];
 #pragma unroll
-                            for (int e = 0; e < 16; ++e) { g[e] = rna_tf32(v[e]); sm[e] = rna_tf32(v[e] - __uint_as_float(g[e])); }
+                        for (int e = 0; e < 8; ++e) {
+                            if (PRECISE) split2_f16(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+                            else split2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+                        }
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const uint32_t off = (uint32_t)(4 * half + q) * LBO + (uint32_t)r * 16u;
-                                sts4(pl0 + off, g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]);
-                                sts4(pl1 + off, sm[4 * q], sm[4 * q + 1], sm[4 * q + 2], sm[4 * q + 3]);
-                            }
-                        } else {
-                            // 16 channels = 2 chunks of 8 bf16; chunk index within the 64-channel block = 4*hb + 2*half + q
-                            uint32_t hi[8], lo[8];
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) split2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
-#pragma unroll
-                            for (int q = 0; q < 2; ++q) {
-                                const uint32_t off = (uint32_t)(4 * hb + 2 * half + q) * LBO + (uint32_t)r * 16u;
-                                sts4(pl0 + off, hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-                                sts4(pl1 + off, lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
-                            }
+                        for (int q = 0; q < 2; ++q) {
+                            const uint32_t off = (uint32_t)(4 * hb + 2 * half + q) * LBO + (uint32_t)r * 16u;
+                            sts4(pl0 + off, hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+                            sts4(pl1 + off, lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
                         }
                     }
                     __syncwarp();
@@ -281,10 +277,12 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
                     tc_fence_after();
 #pragma unroll
                     for (int c = 0; c < COLS / 16; ++c) {
-                        uint32_t v[16];
-                        tmem_ld16(tmem_d + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(abuf * BN + cstart + c * 16), v);
+                        uint32_t v[16], v2[16];
+                        const uint32_t col = (uint32_t)(abuf * C::ACC_COLS + cstart + c * 16);
+                        tmem_ld16(tmem_d + ((uint32_t)(q4 * 32) << 16) + col, v);
+                        tmem_ld16(tmem_d + ((uint32_t)(q4 * 32) << 16) + col + BN, v2);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) racc[c * 16 + j] += __uint_as_float(v[j]);
+                        for (int j = 0; j < 16; ++j) racc[c * 16 + j] += fmaf(__uint_as_float(v2[j]), 1.f / 2048.f, __uint_as_float(v[j]));
                     }
                     tc_fence_before();
                     __syncwarp();
@@ -297,8 +295,10 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
             tc_fence_after();
 #pragma unroll 1
             for (int c = 0; c < COLS / 16; ++c) {
-                uint32_t v[16];
-                tmem_ld16(tmem_d + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(abuf * BN + cstart + c * 16), v);
+                uint32_t v[16], v2[16];
+                const uint32_t col = (uint32_t)(abuf * C::ACC_COLS + cstart + c * 16);
+                tmem_ld16(tmem_d + ((uint32_t)(q4 * 32) << 16) + col, v);
+                if (PRECISE) tmem_ld16(tmem_d + ((uint32_t)(q4 * 32) << 16) + col + BN, v2);
 #pragma unroll
                 for (int j = 0; j < 16; j += 4) {
                     float o[4];
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
                     for (int e = 0; e < 4; ++e) {
                         const int co = n0 + cstart + c * 16 + j + e;
                         float val = __uint_as_float(v[j + e]);
-                        if (PRECISE) val += racc[(PRECISE ? c * 16 + j + e : 0)];
+                        if (PRECISE) val += fmaf(__uint_as_float(v2[j + e]), 1.f / 2048.f, racc[(PRECISE ? c * 16 + j + e : 0)]);
                         if (p.out_scale) val *= __ldg(p.out_scale + (long long)b0 * p.co + co);
                         if (p.bias) val += __ldg(p.bias + co);
                         val += nz;
@@ -356,12 +356,12 @@ __global__ void conv_pack_halo_kernel(const float* __restrict__ w, unsigned char
             v = w[((long long)o * ci + i) * kk2 + ts] * coef;
         }
         unsigned char* tile = wp + (((size_t)nt * nkb + kb) * kk2 + t) * btile;
-        const int esz = precise ? 4 : 2;
-        const size_t off = (size_t)nl * 128 + ((((kk * esz) >> 4) ^ (nl & 7)) << 4) + ((kk * esz) & 15);
+        const size_t off = (size_t)nl * 128 + ((((kk * 2) >> 4) ^ (nl & 7)) << 4) + ((kk * 2) & 15);
         if (precise) {
-            const uint32_t big = rna_tf32(v), small = rna_tf32(v - __uint_as_float(big));
-            *reinterpret_cast<uint32_t*>(tile + off) = big;
-            *reinterpret_cast<uint32_t*>(tile + (size_t)bn * 128 + off) = small;
+            const __half big = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+            const __half small = __float2half_rn((v - __half2float(big)) * 2048.f);
+            *reinterpret_cast<__half*>(tile + off) = big;
+            *reinterpret_cast<__half*>(tile + (size_t)bn * 128 + off) = small;
         } else {
             const __nv_bfloat16 h = __float2bfloat16_rn(v);
             const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
@@ -383,7 +383,7 @@ static int launch(const CUtensorMap& map, const Params& tp, dim3 grid, cudaStrea
         configured = true;
     }
     conv_halo_kernel<BN, PRECISE><<<grid, C::NTHREADS, C::SMEM, st>>>(map, tp);
-    return launched(PRECISE ? "conv_halo_tf32x3" : "conv_halo_bf16x3");
+    return launched(PRECISE ? "conv_halo_fp16x3" : "conv_halo_bf16x3");
 }
 
 }  // namespace halo
@@ -402,8 +402,8 @@ long long conv_packed_bytes_halo(int co, int ci, int k) {
         const int cin = tr ? co : ci, cout = tr ? ci : co;
         const int bn = halo::pick_bn(cout);
         if (!bn || cin % 32) continue;
-        const long long nkb32 = (cin + 31) / 32;              // precise: 32-channel blocks (the larger of the two packs)
-        const long long b = (long long)(cout / bn) * nkb32 * k * k * 2 * bn * 128;
+        const long long nkb = (cin + 63) / 64;
+        const long long b = (long long)(cout / bn) * nkb * k * k * 2 * bn * 128;
         if (b > best) best = b;
     }
     return best;
@@ -413,7 +413,7 @@ int conv_pack_halo(const float* w, void* wp, int co, int ci, int k, float coef, 
     const int cin = transpose ? co : ci, cout = transpose ? ci : co;
     const int bn = halo::pick_bn(cout);
     if (!bn || cin % 32) return fail(SG2_ENOTSUP, "conv_pack_halo: unsupported shape");
-    const int kbs = precise ? 32 : 64;
+    const int kbs = 64;
     const int nkb = (cin + kbs - 1) / kbs;
     const long long total = (long long)(cout / bn) * nkb * k * k * bn * kbs;
     const int blocks = (int)std::min<long long>(ceil_div(total, 256), (long long)num_sms() * 8);
@@ -437,8 +437,7 @@ int conv_fwd_halo(const ConvParams& p, int precise, cudaStream_t st) {
     tp.m_tiles = tp.tiles_x * tp.tiles_y * p.n;
     const int bn = halo::pick_bn(p.co);
     tp.n_tiles = p.co / bn;
-    const int kbs = precise ? 32 : 64;
-    tp.nkb = (p.ci + kbs - 1) / kbs;
+    tp.nkb = (p.ci + 63) / 64;
     tp.act = p.act; tp.alpha = p.alpha; tp.gain = p.gain;
     dim3 grid((unsigned)std::min(tp.m_tiles * tp.n_tiles, num_sms()));
     if (precise) {

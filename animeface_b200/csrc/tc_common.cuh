@@ -113,6 +113,19 @@ __device__ __forceinline__ void sts4(uint32_t addr, uint32_t a, uint32_t b, uint
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// kind::f16 with fp16 operands (a_format = b_format = 0), K-major
+__host__ __device__ constexpr uint32_t idesc_f16(int m, int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// fp16 big/small split of two floats: big = rn_f16(v) (saturating), small = rn_f16((v - big) * 2^11).
+// big carries 11 mantissa bits, the scaled residual the next 11: together 22 bits like the tf32 pair, at the fp16/bf16
+// MMA rate.  The 2^11 keeps the residual in the normal fp16 range; the consumer multiplies the cross-term sum by 2^-11.
+__device__ __forceinline__ void split2_f16(float a, float b, uint32_t& big, uint32_t& small) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(big) : "f"(b), "f"(a));        // {b (high), a (low)}
+    const float2 bf = __half22float2(*reinterpret_cast<const __half2*>(&big));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(small) : "f"((b - bf.y) * 2048.f), "f"((a - bf.x) * 2048.f));
+}
+
 // split two floats into packed bf16x2 hi and lo words (element 0 in the low half)
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
