@@ -19,11 +19,11 @@ template <class T> struct BAcc { typedef float type; };
 template <> struct BAcc<double> { typedef double type; };
 
 // One element.  A = activation index (1..9), G = p.grad at run time.
-template <int A, class S>
-__device__ __forceinline__ S bias_act_eval(S x, S b, S xref, S yref, S dy, int G, S alpha, S gain, S clamp) {
+template <int A, int G, class S>
+__device__ __forceinline__ S bias_act_eval(S x, S b, S xref, S yref, S dy, S alpha, S gain, S clamp) {
     const S one = (S)1, two = (S)2, exp_range = (S)80, half_exp_range = (S)40;
     const S selu_scale = (S)1.0507009873554804934193349852946, selu_alpha = (S)1.6732632423543772848170429916717;
-    S yy = (gain != 0) ? yref / gain : (S)0;
+    S yy = (G != 0 && gain != 0) ? yref / gain : (S)0;      // only the gradient modes look at the saved output
     S y = 0;
     if (G == 0) x += b; else xref += b;
     if (A == 1) { if (G == 0 || G == 1) y = x; }
@@ -71,46 +71,60 @@ __device__ __forceinline__ S bias_act_eval(S x, S b, S xref, S yref, S dy, int G
     return y;
 }
 
-template <class T, int A>
+template <class T, int A, int G>
 __global__ void __launch_bounds__(256) bias_act_scalar(BiasActParams p) {
     typedef typename BAcc<T>::type S;
     const T* x = (const T*)p.x; const T* b = (const T*)p.b; const T* xr = (const T*)p.xref;
     const T* yr = (const T*)p.yref; const T* dy = (const T*)p.dy; T* y = (T*)p.y;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.numel; i += (long long)gridDim.x * blockDim.x) {
         S bv = b ? (S)b[(i / p.step_b) % p.size_b] : (S)0;
-        S v = bias_act_eval<A, S>((S)x[i], bv, xr ? (S)xr[i] : (S)0, yr ? (S)yr[i] : (S)0, dy ? (S)dy[i] : (S)1,
-                                  p.grad, (S)p.alpha, (S)p.gain, (S)p.clamp);
+        S v = bias_act_eval<A, G, S>((S)x[i], bv, xr ? (S)xr[i] : (S)0, yr ? (S)yr[i] : (S)0, dy ? (S)dy[i] : (S)1,
+                                     (S)p.alpha, (S)p.gain, (S)p.clamp);
         y[i] = (T)v;
     }
 }
 
 // fp32, 4 elements per thread.  BMODE 0: no bias, 1: channels_last (step_b == 1, size_b % 4 == 0),
 // 2: step_b % 4 == 0 (the 4 elements share one bias value).
-template <int A, int BMODE>
+template <int A, int G, int BMODE>
 __global__ void __launch_bounds__(256) bias_act_vec4(BiasActParams p) {
     const float* x = (const float*)p.x; const float* b = (const float*)p.b; const float* xr = (const float*)p.xref;
     const float* yr = (const float*)p.yref; const float* dy = (const float*)p.dy; float* y = (float*)p.y;
-    const long long nq = p.numel >> 2;
-    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nq; q += (long long)gridDim.x * blockDim.x) {
-        const long long i = q << 2;
-        float4 xv = ldg4(x + i);
-        float4 bv = f4zero();
-        if (BMODE == 1) bv = ldg4(b + (i % p.size_b));
-        if (BMODE == 2) { float s = __ldg(b + (i / p.step_b) % p.size_b); bv = make_float4(s, s, s, s); }
-        float4 xrv = xr ? ldg4(xr + i) : f4zero();
-        float4 yrv = yr ? ldg4(yr + i) : f4zero();
-        float4 dyv = dy ? ldg4(dy + i) : make_float4(1.f, 1.f, 1.f, 1.f);
-        float4 o;
-        o.x = bias_act_eval<A, float>(xv.x, bv.x, xrv.x, yrv.x, dyv.x, p.grad, p.alpha, p.gain, p.clamp);
-        o.y = bias_act_eval<A, float>(xv.y, bv.y, xrv.y, yrv.y, dyv.y, p.grad, p.alpha, p.gain, p.clamp);
-        o.z = bias_act_eval<A, float>(xv.z, bv.z, xrv.z, yrv.z, dyv.z, p.grad, p.alpha, p.gain, p.clamp);
-        o.w = bias_act_eval<A, float>(xv.w, bv.w, xrv.w, yrv.w, dyv.w, p.grad, p.alpha, p.gain, p.clamp);
-        st4(y + i, o);
+    const int nq = (int)(p.numel >> 2);               // numel <= INT_MAX (checked by the caller): 32-bit index math
+    const int size_b = p.size_b, step_b = (int)p.step_b;
+    constexpr int U = 4;                              // independent 128-bit accesses in flight per thread
+    for (int q0 = blockIdx.x * blockDim.x * U + threadIdx.x; q0 < nq; q0 += gridDim.x * blockDim.x * U) {
+        float4 xv[U], xrv[U], yrv[U], dyv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int q = q0 + u * blockDim.x;
+            if (q < nq) {
+                xv[u] = ldg4(x + 4 * (size_t)q);
+                xrv[u] = xr ? ldg4(xr + 4 * (size_t)q) : f4zero();
+                yrv[u] = yr ? ldg4(yr + 4 * (size_t)q) : f4zero();
+                dyv[u] = dy ? ldg4(dy + 4 * (size_t)q) : make_float4(1.f, 1.f, 1.f, 1.f);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int q = q0 + u * blockDim.x;
+            if (q >= nq) continue;
+            const unsigned i = 4u * (unsigned)q;
+            float4 bv = f4zero();
+            if (BMODE == 1) bv = ldg4(b + (i % (unsigned)size_b));
+            if (BMODE == 2) { float s = __ldg(b + (i / (unsigned)step_b) % (unsigned)size_b); bv = make_float4(s, s, s, s); }
+            float4 o;
+            o.x = bias_act_eval<A, G, float>(xv[u].x, bv.x, xrv[u].x, yrv[u].x, dyv[u].x, p.alpha, p.gain, p.clamp);
+            o.y = bias_act_eval<A, G, float>(xv[u].y, bv.y, xrv[u].y, yrv[u].y, dyv[u].y, p.alpha, p.gain, p.clamp);
+            o.z = bias_act_eval<A, G, float>(xv[u].z, bv.z, xrv[u].z, yrv[u].z, dyv[u].z, p.alpha, p.gain, p.clamp);
+            o.w = bias_act_eval<A, G, float>(xv[u].w, bv.w, xrv[u].w, yrv[u].w, dyv[u].w, p.alpha, p.gain, p.clamp);
+            st4_cs(y + 4 * (size_t)q, o);
+        }
     }
 }
 
-template <int A>
-static int bias_act_dispatch(const BiasActParams& p, int dtype, cudaStream_t st) {
+template <int A, int G>
+static int bias_act_dispatch_g(const BiasActParams& p, int dtype, cudaStream_t st) {
     const int threads = 256;
     auto aligned = [](const void* q) { return q == nullptr || ((uintptr_t)q % 16) == 0; };
     if (dtype == SG2_F32 && (p.numel % 4) == 0 && aligned(p.x) && aligned(p.b) && aligned(p.xref) &&
@@ -120,18 +134,25 @@ static int bias_act_dispatch(const BiasActParams& p, int dtype, cudaStream_t st)
         else if (p.step_b == 1 && p.size_b % 4 == 0) bmode = 1;
         else if (p.step_b % 4 == 0) bmode = 2;
         if (bmode >= 0) {
-            int blocks = (int)std::min<long long>(ceil_div(p.numel / 4, threads), (long long)num_sms() * 16);
-            if (bmode == 0)      bias_act_vec4<A, 0><<<blocks, threads, 0, st>>>(p);
-            else if (bmode == 1) bias_act_vec4<A, 1><<<blocks, threads, 0, st>>>(p);
-            else                 bias_act_vec4<A, 2><<<blocks, threads, 0, st>>>(p);
+            int blocks = (int)std::min<long long>(ceil_div(p.numel / 4, threads * 4), (long long)num_sms() * 16);
+            if (bmode == 0)      bias_act_vec4<A, G, 0><<<blocks, threads, 0, st>>>(p);
+            else if (bmode == 1) bias_act_vec4<A, G, 1><<<blocks, threads, 0, st>>>(p);
+            else                 bias_act_vec4<A, G, 2><<<blocks, threads, 0, st>>>(p);
             return launched("bias_act_vec4");
         }
     }
     int blocks = (int)std::min<long long>(ceil_div(p.numel, threads), (long long)num_sms() * 32);
-    if (dtype == SG2_F32)      bias_act_scalar<float, A><<<blocks, threads, 0, st>>>(p);
-    else if (dtype == SG2_F16) bias_act_scalar<__half, A><<<blocks, threads, 0, st>>>(p);
-    else                       bias_act_scalar<double, A><<<blocks, threads, 0, st>>>(p);
+    if (dtype == SG2_F32)      bias_act_scalar<float, A, G><<<blocks, threads, 0, st>>>(p);
+    else if (dtype == SG2_F16) bias_act_scalar<__half, A, G><<<blocks, threads, 0, st>>>(p);
+    else                       bias_act_scalar<double, A, G><<<blocks, threads, 0, st>>>(p);
     return launched("bias_act_scalar");
+}
+
+template <int A>
+static int bias_act_dispatch(const BiasActParams& p, int dtype, cudaStream_t st) {
+    if (p.grad == 0) return bias_act_dispatch_g<A, 0>(p, dtype, st);
+    if (p.grad == 1) return bias_act_dispatch_g<A, 1>(p, dtype, st);
+    return bias_act_dispatch_g<A, 2>(p, dtype, st);
 }
 
 }  // namespace sg2

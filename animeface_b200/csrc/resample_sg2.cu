@@ -158,6 +158,102 @@ __global__ void __launch_bounds__(256) up2x_adj_kernel(const float* __restrict__
     }
 }
 
+
+// ---- channels_last strip kernels: a block owns (image, an x range, a strip of ROWS input rows); a thread owns one
+// x position x 4 channels and walks down the strip keeping the horizontally filtered rows in registers, so every
+// input row is loaded once (3 x 128-bit loads per input pixel forward, 12 per output pixel for the adjoint) and all
+// index arithmetic is 32-bit and hoisted out of the loop.
+constexpr int kStripRows = 16;
+
+struct H2 { float4 a, b; };     // the two horizontal phases (outputs 2ix, 2ix+1) of one input row
+
+__global__ void __launch_bounds__(256) up2x_fwd_strip_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                             const float* __restrict__ scale, int c, int h, int w, int blur) {
+    const int cq = c >> 2, xs = 256 / cq;
+    const int q = threadIdx.x % cq, ix = blockIdx.x * xs + threadIdx.x / cq;
+    if (ix >= w) return;
+    const int img = blockIdx.z, iy0 = blockIdx.y * kStripRows, iy1 = min(h, iy0 + kStripRows);
+    const int xm = max(ix - 1, 0), xp = min(ix + 1, w - 1);
+    float wx0[3], wx1[3];
+    axis_w(2 * ix, w, blur, wx0); axis_w(2 * ix + 1, w, blur, wx1);
+    const float* xi = x + (size_t)img * h * w * c + 4 * q;
+    float* yi = y + (size_t)img * 4 * h * w * c + 4 * q;
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (scale) sc = ldg4(scale + (size_t)img * c + 4 * q);
+    auto hrow = [&](int iy) {
+        const float* r = xi + (size_t)iy * w * c;
+        const float4 vm = ldg4(r + xm * c), v0 = ldg4(r + ix * c), vp = ldg4(r + xp * c);
+        H2 o;
+        o.a = scale4(vm, wx0[0]); fma4(o.a, wx0[1], v0); fma4(o.a, wx0[2], vp);
+        o.b = scale4(vm, wx1[0]); fma4(o.b, wx1[1], v0); fma4(o.b, wx1[2], vp);
+        o.a = mul4(o.a, sc); o.b = mul4(o.b, sc);
+        return o;
+    };
+    H2 A = hrow(max(iy0 - 1, 0)), B = hrow(iy0);
+    const int ow_c = 2 * w * c;
+    for (int iy = iy0; iy < iy1; ++iy) {
+        const H2 Cn = hrow(min(iy + 1, h - 1));
+        float wy0[3], wy1[3];
+        axis_w(2 * iy, h, blur, wy0); axis_w(2 * iy + 1, h, blur, wy1);
+        float4 o00 = scale4(A.a, wy0[0]), o01 = scale4(A.b, wy0[0]), o10 = scale4(A.a, wy1[0]), o11 = scale4(A.b, wy1[0]);
+        fma4(o00, wy0[1], B.a); fma4(o01, wy0[1], B.b); fma4(o10, wy1[1], B.a); fma4(o11, wy1[1], B.b);
+        fma4(o00, wy0[2], Cn.a); fma4(o01, wy0[2], Cn.b); fma4(o10, wy1[2], Cn.a); fma4(o11, wy1[2], Cn.b);
+        float* o = yi + (size_t)(2 * iy) * ow_c + (size_t)(2 * ix) * c;
+        st4_cs(o, o00); st4_cs(o + c, o01);
+        st4_cs(o + ow_c, o10); st4_cs(o + ow_c + c, o11);
+        A = B; B = Cn;
+    }
+}
+
+__global__ void __launch_bounds__(256) up2x_adj_strip_kernel(const float* __restrict__ gy, float* __restrict__ gx,
+                                                             const float* __restrict__ scale, int c, int h, int w, int blur) {
+    const int cq = c >> 2, xs = 256 / cq;
+    const int q = threadIdx.x % cq, ix = blockIdx.x * xs + threadIdx.x / cq;
+    if (ix >= w) return;
+    const int img = blockIdx.z, iy0 = blockIdx.y * kStripRows, iy1 = min(h, iy0 + kStripRows);
+    const int OH = 2 * h, OW = 2 * w;
+    float Ax[6];
+    axis_w_adj(ix, w, blur, Ax);
+    const float* gi = gy + (size_t)img * 4 * h * w * c + 4 * q;
+    // column offsets clamped into the image (weights of out-of-range columns are zeroed) so that the 6 loads of a row
+    // are unconditional and can all be in flight together
+    int jxo[6];
+#pragma unroll
+    for (int b = 0; b < 6; ++b) {
+        const int jx = 2 * ix - 2 + b;
+        if (jx < 0 || jx >= OW) Ax[b] = 0.f;
+        jxo[b] = min(max(jx, 0), OW - 1) * c;
+    }
+    // horizontally reduced row jy of gy (zero outside the image)
+    auto hrow = [&](int jy) {
+        const float keep = (jy >= 0 && jy < OH) ? 1.f : 0.f;
+        const float* row = gi + (size_t)min(max(jy, 0), OH - 1) * OW * c;
+        float4 v[6];
+#pragma unroll
+        for (int b = 0; b < 6; ++b) v[b] = ldg4(row + jxo[b]);
+        float4 r = scale4(v[0], Ax[0] * keep);
+#pragma unroll
+        for (int b = 1; b < 6; ++b) fma4(r, Ax[b] * keep, v[b]);
+        return r;
+    };
+    float4 H[6];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) H[a + 2] = hrow(2 * iy0 - 2 + a);      // rows 2iy0-2 .. 2iy0+1 sit in H[2..5] before the first shift
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (scale) sc = ldg4(scale + (size_t)img * c + 4 * q);
+    float* go = gx + (size_t)img * h * w * c + 4 * q;
+    for (int iy = iy0; iy < iy1; ++iy) {
+        H[0] = H[2]; H[1] = H[3]; H[2] = H[4]; H[3] = H[5];
+        H[4] = hrow(2 * iy + 2); H[5] = hrow(2 * iy + 3);
+        float Ay[6];
+        axis_w_adj(iy, h, blur, Ay);
+        float4 acc = f4zero();
+#pragma unroll
+        for (int a = 0; a < 6; ++a) fma4(acc, Ay[a], H[a]);
+        st4_cs(go + ((size_t)iy * w + ix) * c, mul4(acc, sc));
+    }
+}
+
 // y = alpha * (avg2x2(x) + avg2x2(t)),  NHWC, one thread = one output pixel x 4 channels.
 __global__ void __launch_bounds__(256) avgpool2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ t,
                                                            float* __restrict__ y, float alpha, int n, int c, int h, int w) {
@@ -208,6 +304,14 @@ static int up2x_launch(bool adj, const float* a, float* b, const float* scale, i
     if (nhwc && !vec) return fail(SG2_ENOTSUP, "up2x: channels_last path needs C %% 4 == 0 and 16-byte aligned pointers (C=%d)", c);
     if (nhwc) { g.imgs = n; g.lanes = c / 4; g.pix_stride = c; g.lane_stride = 4; }
     else      { g.imgs = n * c; g.lanes = 1; g.pix_stride = 1; g.lane_stride = 0; }
+    const int cq = c / 4;
+    if (nhwc && cq >= 1 && cq <= 256 && (256 % cq) == 0) {
+        const int xs = 256 / cq;
+        dim3 grid((unsigned)ceil_div(w, xs), (unsigned)ceil_div(h, kStripRows), (unsigned)n);
+        if (adj) up2x_adj_strip_kernel<<<grid, 256, 0, st>>>(a, b, scale, c, h, w, blur);
+        else     up2x_fwd_strip_kernel<<<grid, 256, 0, st>>>(a, b, scale, c, h, w, blur);
+        return launched(adj ? "up2x_adj_strip" : "up2x_fwd_strip");
+    }
     const long long total = (long long)g.imgs * h * w * g.lanes;
     const int threads = 256;
     const int blocks = (int)std::min<long long>(ceil_div(total, threads), (long long)num_sms() * 16);

@@ -112,6 +112,51 @@ __global__ void __launch_bounds__(256) upfirdn2d_vec4_nhwc(UpfirdnParams p) {
     }
 }
 
+
+// Strip version of the channels_last fast path: block = (x range, strip of output rows, image); a thread owns one output
+// column x 4 channels and walks down the strip.  All index math is 32-bit; the x-direction tap range is hoisted.
+constexpr int kUpfStrip = 8;
+
+__global__ void __launch_bounds__(256) upfirdn2d_strip_nhwc(UpfirdnParams p) {
+    __shared__ float sf[kMaxTaps];
+    for (int i = threadIdx.x; i < p.fh * p.fw; i += blockDim.x) {
+        int ty = i / p.fw, tx = i % p.fw;
+        int fy = p.flip ? ty : p.fh - 1 - ty, fx = p.flip ? tx : p.fw - 1 - tx;
+        sf[i] = p.f[fy * p.fw + fx] * p.gain;
+    }
+    __syncthreads();
+    const int cq = p.c >> 2, xs = 256 / cq;
+    const int q = threadIdx.x % cq, jx = blockIdx.x * xs + threadIdx.x / cq;
+    if (jx >= p.out_w) return;
+    const int img = blockIdx.z, jy0 = blockIdx.y * kUpfStrip, jy1 = min(p.out_h, jy0 + kUpfStrip);
+    const float* __restrict__ x = (const float*)p.x + (size_t)img * p.xs[0] + 4 * q;
+    float* __restrict__ y = (float*)p.y + (size_t)img * p.ys[0] + 4 * q;
+    const int xrow = (int)p.xs[2], xpix = (int)p.xs[3], yrow = (int)p.ys[2], ypix = (int)p.ys[3];
+    // x-direction taps of this column: tx = txa + k*upx, input column ixa + k, k in [0, nx)
+    const int basex = jx * p.downx - p.padx0;
+    int txa = pos_mod(-basex, p.upx);
+    int ixa = (basex + txa) / p.upx;              // exact division (may be negative)
+    if (ixa < 0) { txa += -ixa * p.upx; ixa = 0; }
+    int nx = txa < p.fw ? (p.fw - 1 - txa) / p.upx + 1 : 0;
+    nx = min(nx, p.in_w - ixa);
+    for (int jy = jy0; jy < jy1; ++jy) {
+        const int basey = jy * p.downy - p.pady0;
+        int tya = pos_mod(-basey, p.upy);
+        int iya = (basey + tya) / p.upy;
+        if (iya < 0) { tya += -iya * p.upy; iya = 0; }
+        int ny = tya < p.fh ? (p.fh - 1 - tya) / p.upy + 1 : 0;
+        ny = min(ny, p.in_h - iya);
+        float4 acc = f4zero();
+        for (int a = 0; a < ny; ++a) {
+            const float* xr = x + (size_t)(iya + a) * xrow + (size_t)ixa * xpix;
+            const float* fr = sf + (tya + a * p.upy) * p.fw + txa;
+#pragma unroll 4
+            for (int b = 0; b < nx; ++b) fma4(acc, fr[b * p.upx], ldg4(xr + (size_t)b * xpix));
+        }
+        st4_cs(y + (size_t)jy * yrow + (size_t)jx * ypix, acc);
+    }
+}
+
 }  // namespace sg2
 
 using namespace sg2;
@@ -159,6 +204,13 @@ extern "C" int sg2_upfirdn2d(const void* x, const float* f, void* y, int dtype,
                             p.xs[3] == c && p.ys[3] == c && p.xs[2] == (long long)in_w * c &&
                             p.ys[2] == (long long)out_w * c && (p.xs[0] % 4) == 0 && (p.ys[0] % 4) == 0 &&
                             ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0;
+    const int cq = c / 4;
+    if (dtype == SG2_F32 && nhwc_dense && fh * fw <= kMaxTaps && cq <= 256 && (256 % cq) == 0 && n <= 65535) {
+        const int xs = 256 / cq;
+        dim3 grid((unsigned)ceil_div(out_w, xs), (unsigned)ceil_div(out_h, kUpfStrip), (unsigned)n);
+        upfirdn2d_strip_nhwc<<<grid, threads, 0, st>>>(p);
+        return launched("upfirdn2d_strip_nhwc");
+    }
     if (dtype == SG2_F32 && nhwc_dense && fh * fw <= kMaxTaps) {
         long long work = total / 4;
         int blocks = (int)std::min<long long>(ceil_div(work, threads), (long long)num_sms() * 32);

@@ -23,6 +23,7 @@ import torch.nn.functional as F
 
 from . import rng
 from .ops import conv2d as C
+from .ops.bias_act import bias_act
 from .ops.mbstd import minibatch_stddev
 from .ops.resample import avgpool2, upsample2x_bilinear, upsample2x_blur
 
@@ -328,6 +329,18 @@ class Discriminator(nn.Module):
         while i < len(mods):
             m = mods[i]
             fuse = i + 1 < len(mods) and isinstance(mods[i + 1], nn.LeakyReLU)
+            if (isinstance(m, MiniBatchStdDev) and i + 2 < len(mods) and isinstance(mods[i + 1], ELR)
+                    and isinstance(mods[i + 1].layer, nn.Conv2d) and isinstance(mods[i + 2], nn.LeakyReLU) and x.shape[1] % 32 == 0):
+                # conv over [x, stddev] (C+1 = 513 channels) = conv(x, W[:, :C]) + conv(stddev map, W[:, C:]): the first
+                # term runs on the tensor cores (C is a multiple of 32), the one-channel term is a trivial fp32 conv.
+                conv = mods[i + 1]
+                c_in = x.shape[1]
+                y = m(x)
+                w = conv.layer.weight
+                z = C.conv2d(x, w[:, :c_in].contiguous(), conv.coef) + C.conv2d(y[:, c_in:], w[:, c_in:].contiguous(), conv.coef)
+                x = bias_act(z, conv.layer.bias, act='lrelu', alpha=SLOPE, gain=1.0)
+                i += 3
+                continue
             if isinstance(m, ELR) and isinstance(m.layer, nn.Conv2d):
                 x = C.conv2d_bias_act(x, m.layer.weight, m.layer.bias, m.coef, SLOPE if fuse else None)
                 i += 2 if fuse else 1

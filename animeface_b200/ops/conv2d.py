@@ -223,15 +223,35 @@ class ConvBiasActFn(torch.autograd.Function):
     def backward(ctx, gy):
         from .bias_act import act_grad
         x, w, y = ctx.saved_tensors
-        gu = act_grad(gy, y, ctx.slope) if ctx.slope is not None else gy
-        gx = gw = gb = None
+        co = w.shape[0]
+        gb = None
+        if torch.is_grad_enabled() or co % 4 != 0:
+            # create_graph (R1): every piece must stay differentiable
+            gu = act_grad(gy, y, ctx.slope) if ctx.slope is not None else gy
+            if ctx.needs_input_grad[2]:
+                gb = gu.sum((0, 2, 3))
+        else:
+            # first-order backward: leaky-ReLU mask and the bias-gradient reduction in ONE pass over (gy, y)
+            lib = _lib.load()
+            n, _, h, wd = gy.shape
+            gyc = _cl(gy)
+            part = torch.empty((n, co), dtype=torch.float32, device=gy.device)
+            if ctx.slope is not None:
+                gu = _empty_cl(n, co, h, wd, gy)
+                _lib.check(lib.sg2_modconv_bwd_prep(gyc.data_ptr(), _cl(y).data_ptr(), None, None, None, gu.data_ptr(),
+                                                    part.data_ptr(), None, n, h * wd, co, float(ctx.slope),
+                                                    _lib.stream_ptr(gy)), 'sg2_modconv_bwd_prep')
+            else:
+                gu = gyc
+                _lib.check(lib.sg2_reduce_hw(gyc.data_ptr(), None, part.data_ptr(), n, h * wd, co, _lib.stream_ptr(gy)),
+                           'sg2_reduce_hw')
+            gb = part.sum(0)
+        gx = gw = None
         if ctx.needs_input_grad[0]:
             gx = Conv2dTransposeFn.apply(gu, w, ctx.coef)
         if ctx.needs_input_grad[1]:
             gw = Conv2dWgradFn.apply(x, gu, w.shape[2], ctx.coef)
-        if ctx.needs_input_grad[2]:
-            gb = gu.sum((0, 2, 3))
-        return gx, gw, gb, None, None
+        return gx, gw, (gb if ctx.needs_input_grad[2] else None), None, None
 
 
 def conv2d_bias_act(x, w, b, coef: float = 1.0, slope: float | None = 0.2):
