@@ -261,8 +261,9 @@ def conv2d_bias_act(x, w, b, coef: float = 1.0, slope: float | None = 0.2):
 
 
 # ----------------------------------------------------------------------------------------------
-# Modulated convolution (generator).  First-order autograd; the per-sample weight tensor
-# [B, Co, Ci, k, k] of the reference (model.py:115-120) is never materialised.
+# Modulated convolution (generator).  The per-sample weight tensor [B, Co, Ci, k, k] of the reference
+# (model.py:115-120) is never materialised.  ModConvFn is the fused first-order path of every ordinary step;
+# path-length steps run the any-order composition below (same arithmetic, separate kernels).
 
 class ModConvFn(torch.autograd.Function):
     @staticmethod
@@ -322,6 +323,39 @@ class ModConvFn(torch.autograd.Function):
         return gx, gw, gs, gd, (gb if b is not None else None), None, None, None, None
 
 
+_any_order = False
+
+
+class any_order_modconv:
+    """Context manager: inside it ``modulated_conv2d`` is composed from the closed convolution family, the
+    twice-differentiable ``bias_act`` and torch broadcasts, so gradients of ANY order exist -- what the
+    path-length regulariser needs (second order through the modulated convolution w.r.t. the style,
+    implementations/StyleGAN2/utils.py:18-29).  Outside it the fused first-order ``ModConvFn`` runs."""
+
+    def __enter__(self):
+        global _any_order
+        self._prev, _any_order = _any_order, True
+        return self
+
+    def __exit__(self, *exc):
+        global _any_order
+        _any_order = self._prev
+
+
+def _modulated_conv2d_any_order(x, w, s, d, bias, noise, coef, slope):
+    from .bias_act import bias_act
+    acc = Conv2dFn.apply(x * s[:, :, None, None], w, coef, True)
+    if d is not None:
+        acc = acc * d[:, :, None, None]
+    if bias is not None:
+        acc = acc + bias
+    if noise is not None:
+        acc = acc + noise
+    if slope is not None:
+        acc = bias_act(acc, None, act='lrelu', alpha=slope, gain=1.0)
+    return acc
+
+
 def modulated_conv2d(x, w, s, bias=None, noise=None, demod=True, slope=None, eps=1e-4, out_nchw=False):
     """ModulatedConv2d.forward (model.py:106-132) (+ InjectNoise :85-88 + LeakyReLU :164 when given).
 
@@ -334,4 +368,6 @@ def modulated_conv2d(x, w, s, bias=None, noise=None, demod=True, slope=None, eps
     if demod:
         wsq = w.square().sum((2, 3))                       # [Co,Ci]
         d = torch.rsqrt(torch.matmul(s.square(), wsq.t()) * (coef * coef) + eps)
+    if _any_order:
+        return _modulated_conv2d_any_order(x, w, s, d, bias, noise, coef, slope)
     return ModConvFn.apply(x, w, s, d, bias, noise, coef, slope, out_nchw)

@@ -8,21 +8,44 @@ the device.  Two equivalences are used (results identical, work skipped):
   * D phase: G runs under no_grad (the reference builds the graph and detaches, :67-69);
   * G phase: D's parameters do not require grad (the reference computes their gradients and then discards them
     at the next ``zero_grad``, :55-56).
-Path-length regularisation (:18-33, 96-103) is off by default in the reference (pl_lambda = 0, :159) and not
-built yet.
+Path-length regularisation (:18-33, 96-103; off by default in the reference, pl_lambda = 0 at :159) runs on steps
+``batches_done % g_k == 0``: the generator forward of that step is built from the any-order modulated convolution
+(ops.conv2d.any_order_modconv) so that d(sum(img * noise))/d style can itself be differentiated; like the reference
+the GAN loss of the generator is dropped on those steps, and the running ``pl_mean`` is the EMA(0.99) of the PENALTY
+value (utils.py:100-103) -- kept as a device scalar here instead of the reference's ``.cpu().numpy()`` round trip.
 """
 from __future__ import annotations
 
+import contextlib
 import functools
+import math
 from dataclasses import dataclass
 
 import torch
 
 from . import rng
+from .ops.conv2d import any_order_modconv
 from .diffaugment import DiffAugment
 from .model import Discriminator, Generator, init_weight_N01, supplied_noise  # noqa: F401
 from .nnutils import FlatAdam, update_ema
-from .nnutils.loss import NonSaturatingLoss, r1_regularizer
+from .nnutils.loss import NonSaturatingLoss, calc_grad, r1_regularizer
+
+
+def pl_penalty(styles, images, pl_mean, scaler=None):
+    """Path-length regulariser (implementations/StyleGAN2/utils.py:18-29): with noise ~ N(0,1)/sqrt(H*W),
+    g = d sum(images * noise) / d styles (create_graph), penalty = mean_b((||g_b||_2 - pl_mean)^2).
+    ``images`` must come from a generator forward run under ``any_order_modconv``."""
+    num_pixels = images.size()[2:].numel()
+    noise = rng.randn(*images.size(), device=images.device) / math.sqrt(num_pixels)
+    outputs = (images * noise).sum()
+    gradients = calc_grad(outputs, styles, scaler)
+    gradients = gradients.pow(2).sum(dim=1).sqrt()
+    return (gradients - pl_mean).pow(2).mean()
+
+
+def update_pl_mean(old, new, decay=0.99):
+    """exponential moving average (implementations/StyleGAN2/utils.py:31-33)"""
+    return decay * old + (1 - decay) * new
 
 
 @dataclass
@@ -84,22 +107,26 @@ class Trainer:
     """One object = the state of the reference's ``train()`` loop; ``step(real)`` = one iteration."""
 
     def __init__(self, cfg: TrainConfig, G, G_ema, D, opt_g, opt_d):
-        if cfg.pl_lambda > 0:
-            raise NotImplementedError('path-length regularisation is not built yet (off by default in the reference)')
         self.cfg, self.G, self.G_ema, self.D, self.opt_g, self.opt_d = cfg, G, G_ema, D, opt_g, opt_d
         self.loss = NonSaturatingLoss()
         self.r1 = r1_regularizer()
         self.augment = functools.partial(DiffAugment, policy=cfg.policy)
         self.batches_done = 0
         self._d_params = list(D.parameters())
+        # running mean of the path-length penalty (utils.py:44, 100-103), on the device so the step never syncs
+        self.pl_mean = torch.zeros((), dtype=torch.float32, device=next(G.parameters()).device)
 
     def is_r1_step(self, it=None):
         it = self.batches_done if it is None else it
         return it % self.cfg.d_k == 0 and self.cfg.r1_lambda > 0 and it != 0
 
-    def step(self, real: torch.Tensor, force_r1=None):
+    def is_pl_step(self, it=None):
+        it = self.batches_done if it is None else it
+        return it % self.cfg.g_k == 0 and self.cfg.pl_lambda > 0 and it != 0
+
+    def step(self, real: torch.Tensor, force_r1=None, force_pl=None):
         """real: [B,3,H,W] on the device.  Returns (D_loss, G_loss, fake) device tensors; no host sync.
-        force_r1 overrides the lazy-regularisation schedule for this call (used to warm up / capture graphs)."""
+        force_r1 / force_pl override the lazy-regularisation schedule for this call (used to warm up / capture graphs)."""
         cfg, G, D = self.cfg, self.G, self.D
         B, dev = real.size(0), real.device
         self.opt_g.zero_grad()
@@ -107,6 +134,7 @@ class Trainer:
         # ---- discriminator phase (utils.py:60-86)
         z = rng.randn(B, cfg.style_dim, device=dev)
         r1_step = self.is_r1_step() if force_r1 is None else bool(force_r1)
+        pl_step = self.is_pl_step() if force_pl is None else bool(force_pl)
         real_aug = self.augment(real)
         with torch.no_grad():
             fake, _ = G(z)
@@ -124,10 +152,22 @@ class Trainer:
         for p in self._d_params:
             p.requires_grad_(False)
         try:
-            fake, _ = G(z)
-            fake_prob = D(self.augment(fake))
-            G_loss = self.loss.g_loss(fake_prob)
-            G_loss.backward()
+            if pl_step:
+                # lazy path-length step (utils.py:96-103): G_loss is the penalty alone; D(fake_aug) of :93-94 is a dead
+                # value, its augmentation draws are still consumed in the reference's order.
+                with any_order_modconv():
+                    fake, style = G(z)
+                with torch.no_grad():
+                    self.augment(fake)
+                pl = pl_penalty(style, fake, self.pl_mean)
+                G_loss = pl * cfg.pl_lambda * cfg.g_k
+                G_loss.backward()
+                self.pl_mean.copy_(update_pl_mean(self.pl_mean, pl.detach()))
+            else:
+                fake, _ = G(z)
+                fake_prob = D(self.augment(fake))
+                G_loss = self.loss.g_loss(fake_prob)
+                G_loss.backward()
         finally:
             for p in self._d_params:
                 p.requires_grad_(True)
@@ -138,30 +178,43 @@ class Trainer:
 
 
 class GraphedTrainer:
-    """``Trainer.step`` captured into CUDA graphs -- one for the normal step, one for the lazy-R1 step -- and replayed.
+    """``Trainer.step`` captured into CUDA graphs -- one per step kind (normal, lazy-R1, and the path-length variants
+    when pl_lambda > 0) -- and replayed.
 
     A step launches ~1300 kernels (convolutions, resampling, elementwise, optimizer); replaying a graph removes the
     Python / launch gaps between them (guide rule: "capture launch-bound inner loops in CUDA graphs").  Everything in
     the step is capture-safe: no host syncs, random draws from the device generator, tensor maps and kernel arguments
-    are functions of addresses that the graph's private memory pool keeps fixed, the Adam step counters live on the
-    device.  Policy: the first step of each kind runs eagerly (it also warms kernels up), the second one is captured
-    and replayed, later ones are replays.  ``prime()`` does that up front for both kinds."""
+    are functions of addresses that the graph's private memory pool keeps fixed, the Adam step counters and the
+    path-length running mean live on the device; under torchrun the NCCL all-reduce of the flat gradient buffer is
+    captured with the rest.  Policy: the first step of each kind runs eagerly (it also warms kernels up), the second
+    one is captured and replayed, later ones are replays.  ``prime()`` does that up front for every kind of the
+    schedule."""
 
     def __init__(self, trainer: Trainer):
         self.t = trainer
         self.static_real = None
-        self.graphs = {}          # kind (is_r1) -> (CUDAGraph, outputs)
+        self.graphs = {}          # kind (is_r1, is_pl) -> (CUDAGraph, outputs)
         self.seen = set()
 
-    def prime(self, real):
-        """Eager + capture for both kinds now (4 extra optimizer steps; two of them are out-of-schedule R1 steps)."""
-        for kind in (False, True):
-            self.step(real, force_r1=kind)
-            self.step(real, force_r1=kind)
+    def kinds(self):
+        """Step kinds of the lazy-regularisation schedule, most frequent first."""
+        t, out = self.t, []
+        for it in range(1, 2 * t.cfg.d_k * t.cfg.g_k + 1):
+            k = (t.is_r1_step(it), t.is_pl_step(it))
+            if k not in out:
+                out.append(k)
+        return out
 
-    def step(self, real, force_r1=None):
+    def prime(self, real):
+        """Eager + capture for every kind now (2 extra optimizer steps per kind, out of schedule)."""
+        for kind in self.kinds():
+            self.step(real, *kind)
+            self.step(real, *kind)
+
+    def step(self, real, force_r1=None, force_pl=None):
         t = self.t
-        kind = t.is_r1_step() if force_r1 is None else bool(force_r1)
+        kind = (t.is_r1_step() if force_r1 is None else bool(force_r1),
+                t.is_pl_step() if force_pl is None else bool(force_pl))
         if self.static_real is None:
             self.static_real = real.clone()
         if kind in self.graphs:
@@ -172,13 +225,13 @@ class GraphedTrainer:
             return out
         if kind not in self.seen:
             self.seen.add(kind)
-            return t.step(real, force_r1=kind)
+            return t.step(real, *kind)
         self.static_real.copy_(real)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         done = t.batches_done
         with torch.cuda.graph(g):
-            out = t.step(self.static_real, force_r1=kind)
+            out = t.step(self.static_real, *kind)
         t.batches_done = done               # capture does not execute: the replay below is the real step
         self.graphs[kind] = (g, out)
         g.replay()

@@ -9,7 +9,8 @@ Restated from (paths relative to the STomoya/animeface checkout):
   generator      implementations/StyleGAN2/model.py:71-135 (MapLinear, InjectNoise, ModulatedConv2d), :154-180,
                  :239-363 (ToImage, PixelNorm, Mapping, Synthesis, Generator)
   discriminator  implementations/StyleGAN2/model.py:186-236, :370-401
-  step           implementations/StyleGAN2/utils.py:53-116 (loop body), :208-221 (Adam set-up)
+  step           implementations/StyleGAN2/utils.py:53-116 (loop body), :208-221 (Adam set-up),
+                 :18-33 (path-length penalty and its running mean)
   losses         nnutils/loss/gan.py:98-114, nnutils/loss/penalty.py:11-26, 85-101
   augmentation   thirdparty/diffaugment/DiffAugment.py:10-53
   ema            nnutils/training.py:23-40
@@ -229,8 +230,16 @@ def r1_penalty(sd_d, real, mbsd_groups=4):
     return g.reshape(g.shape[0], -1).norm(2, dim=1).pow(2).mean() / 2.
 
 
+def pl_penalty(style, image, pl_mean, rng):
+    """implementations/StyleGAN2/utils.py:18-29: noise = randn(image.shape)/sqrt(H*W); g = d sum(image*noise)/d style
+    (create_graph); mean_b((||g_b||_2 - pl_mean)^2)."""
+    noise = rng.randn(*image.shape) / math.sqrt(image.shape[2] * image.shape[3])
+    g, = torch.autograd.grad((image * noise).sum(), style, create_graph=True, retain_graph=True)
+    return (g.pow(2).sum(dim=1).sqrt() - pl_mean).pow(2).mean()
+
+
 # --------------------------------------------------------------------------------------------------------
-# one training step (loop body of implementations/StyleGAN2/utils.py:53-116, AMP off, PL off)
+# one training step (loop body of implementations/StyleGAN2/utils.py:53-116, AMP off)
 
 @dataclass
 class StepConfig:
@@ -243,17 +252,24 @@ class StepConfig:
     lr: float = 1e-3
     betas: tuple = (0., 0.99)
     ema_decay: float = 0.999
+    pl_lambda: float = 0.
+    g_k: int = 8
 
 
 def adam_hparams(cfg: StepConfig):
-    """(g_lr, g_betas, d_lr, d_betas) as utils.py:208-218 with pl_lambda = 0, r1_lambda > 0."""
-    ratio = cfg.d_k / (cfg.d_k + 1)
-    return cfg.lr, cfg.betas, cfg.lr * ratio, (cfg.betas[0] ** ratio, cfg.betas[1] ** ratio)
+    """(g_lr, g_betas, d_lr, d_betas) as utils.py:208-218 (lazy-regularisation ratios k/(k+1) when the penalty is on)."""
+    def scaled(on, k):
+        r = k / (k + 1) if on else 1.0
+        return cfg.lr * r, (cfg.betas[0] ** r, cfg.betas[1] ** r)
+    g_lr, g_b = scaled(cfg.pl_lambda > 0, cfg.g_k)
+    d_lr, d_b = scaled(cfg.r1_lambda > 0, cfg.d_k)
+    return g_lr, g_b, d_lr, d_b
 
 
-def train_step(sd_g, sd_d, sd_ema, opt_g, opt_d, real, step_idx, rng, cfg: StepConfig):
+def train_step(sd_g, sd_d, sd_ema, opt_g, opt_d, real, step_idx, rng, cfg: StepConfig, state=None):
     """sd_* are dicts of leaf tensors (requires_grad=True for G and D); opt_* are torch optimizers over their
-    values.  Returns (D_loss, G_loss, fake) as detached tensors."""
+    values.  ``state`` (a dict) carries ``pl_mean`` across steps when cfg.pl_lambda > 0.
+    Returns (D_loss, G_loss, fake) as detached tensors."""
     B = real.shape[0]
     opt_g.zero_grad()
     opt_d.zero_grad()
@@ -270,8 +286,14 @@ def train_step(sd_g, sd_d, sd_ema, opt_g, opt_d, real, step_idx, rng, cfg: StepC
     opt_d.step()
     # --- generator phase
     z = rng.randn(B, cfg.latent_dim)
-    fake, _ = generator(sd_g, z, rng, cfg.map_lr)
-    g_loss = g_loss_ns(discriminator(sd_d, diffaugment(fake, rng, cfg.policy), cfg.mbsd_groups))
+    fake, style = generator(sd_g, z, rng, cfg.map_lr)
+    fake_prob = discriminator(sd_d, diffaugment(fake, rng, cfg.policy), cfg.mbsd_groups)
+    if step_idx % cfg.g_k == 0 and cfg.pl_lambda > 0 and step_idx != 0:
+        pl = pl_penalty(style, fake, state['pl_mean'], rng)
+        g_loss = pl * cfg.pl_lambda * cfg.g_k
+        state['pl_mean'] = 0.99 * state['pl_mean'] + 0.01 * float(pl.detach())      # EMA of the penalty, utils.py:100-103
+    else:
+        g_loss = g_loss_ns(fake_prob)
     g_loss.backward()
     opt_g.step()
     if sd_ema is not None:

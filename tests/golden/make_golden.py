@@ -10,6 +10,8 @@ that the oracle and the GPU path can replay them.  Files (all small, committed):
     ops.npz      upfirdn2d / bias_act reference ops (thirdparty/stylegan3_ops, impl='ref') incl. gradients
     modules.npz  single StyleGAN2 modules (implementations/StyleGAN2/model.py) forward + gradients
     model.npz    small G/D: images, logits, losses, all parameter gradients, R1, 3-step trajectory
+    pl.npz       path-length penalty (implementations/StyleGAN2/utils.py:18-33): value, per-sample gradient norms,
+                 all second-order parameter gradients, 4-step trajectory with a PL step and an R1 step
 """
 import functools
 import os
@@ -282,9 +284,103 @@ def gen_model():
     print('model.npz', len(out))
 
 
+def gen_pl():
+    """Path-length regulariser through the reference's own pl_penalty / train-loop arithmetic."""
+    from implementations.StyleGAN2.utils import pl_penalty, update_pl_mean
+    c = dict(CFG, d_k=3, g_k=2, pl_lambda=2.)
+    out = {'cfg': np.array(repr(c))}
+    torch.manual_seed(4242)
+    mk = lambda: ref_model.Generator(c['image_size'], c['image_channels'], c['style_dim'], c['channels'], c['max_channels'],
+                                     c['block_num_conv'], c['map_num_layers'], True, 0.01)
+    G, G_ema = mk(), mk()
+    D = ref_model.Discriminator(c['image_size'], c['image_channels'], c['channels'], c['max_channels'],
+                                c['block_num_conv'], c['mbsd_groups'])
+    G.init_weight(map_init_func=functools.partial(ref_model.init_weight_N01, lr=0.01), syn_init_func=ref_model.init_weight_N01)
+    G_ema.eval()
+    G_ema.load_state_dict(G.state_dict())
+    update_ema(G, G_ema, decay=0)
+    D.apply(ref_model.init_weight_N01)
+    for k, v in G.state_dict().items():
+        out['G0.' + k] = A(v)
+    for k, v in D.state_dict().items():
+        out['D0.' + k] = A(v)
+    B = c['batch']
+    # --- one evaluation: value, per-sample norms, parameter gradients of the penalty (second order through G)
+    z = torch.randn(B, c['style_dim'])
+    out['z'] = A(z)
+    pl_mean0 = 0.37
+    out['pl_mean0'] = np.array(pl_mean0, np.float32)
+    with Recorder() as rec:
+        image, style = G(z)
+        pl = pl_penalty(style, image, pl_mean0, None)
+    for i, t in enumerate(rec.items):
+        out[f'eval.draw.{i}'] = A(t)
+    out['eval.n_draws'] = np.array(len(rec.items))
+    out['eval.image'] = A(image); out['eval.pl'] = A(pl)
+    noise = rec.items[-1] / np.sqrt(image.shape[2] * image.shape[3])
+    gnorm = torch.autograd.grad((image * noise).sum(), style, retain_graph=True)[0].pow(2).sum(1).sqrt()
+    out['eval.gnorm'] = A(gnorm)
+    pg = torch.autograd.grad(pl, list(G.parameters()), allow_unused=True)
+    for (n_, p), g_ in zip(G.named_parameters(), pg):
+        out['plgrad.' + n_] = A(g_) if g_ is not None else np.zeros(p.shape, np.float32)
+        out['plnone.' + n_] = np.array(g_ is None)
+    # --- 4-step trajectory, loop body of utils.py:53-116 with pl_lambda > 0: step 2 is a PL step, step 3 an R1 step
+    loss = NonSaturatingLoss()
+    rg, rd = c['g_k'] / (c['g_k'] + 1), c['d_k'] / (c['d_k'] + 1)
+    opt_g = torch.optim.Adam(G.parameters(), lr=c['lr'] * rg, betas=(c['betas'][0] ** rg, c['betas'][1] ** rg))
+    opt_d = torch.optim.Adam(D.parameters(), lr=c['lr'] * rd, betas=(c['betas'][0] ** rd, c['betas'][1] ** rd))
+    augment = functools.partial(DiffAugment, policy='color,translation')
+    r1_loss = r1_regularizer()
+    pl_mean = 0.
+    steps = 4
+    for it in range(steps):
+        real = torch.rand(B, 3, c['image_size'], c['image_size']) * 2 - 1
+        out[f'traj.{it}.real'] = A(real)
+        with Recorder() as rec:
+            opt_g.zero_grad(); opt_d.zero_grad()
+            z = torch.randn(B, c['style_dim'])
+            real_prob = D(augment(real))
+            fake, _ = G(z)
+            fake_prob = D(augment(fake).detach())
+            if it % c['d_k'] == 0 and it != 0:
+                D_loss = r1_loss(real, D, None) * c['r1_lambda'] * c['d_k']
+            else:
+                D_loss = loss.d_loss(real_prob, fake_prob)
+            D_loss.backward(); opt_d.step()
+            z = torch.randn(B, c['style_dim'])
+            fake, style = G(z)
+            fake_prob = D(augment(fake))
+            if it % c['g_k'] == 0 and it != 0:
+                pl = pl_penalty(style, fake, pl_mean, None)
+                G_loss = pl * c['pl_lambda'] * c['g_k']
+                pl_mean = update_pl_mean(pl_mean, np.mean(pl.detach().cpu().numpy()))
+            else:
+                G_loss = loss.g_loss(fake_prob)
+            G_loss.backward(); opt_g.step()
+            update_ema(G, G_ema)
+        for i, t in enumerate(rec.items):
+            out[f'traj.{it}.draw.{i}'] = A(t)
+        out[f'traj.{it}.n_draws'] = np.array(len(rec.items))
+        out[f'traj.{it}.d_loss'] = A(D_loss); out[f'traj.{it}.g_loss'] = A(G_loss); out[f'traj.{it}.fake'] = A(fake)
+        out[f'traj.{it}.pl_mean'] = np.array(pl_mean, np.float32)
+    for k, v in G.state_dict().items():
+        out['G4.' + k] = A(v)
+    for k, v in D.state_dict().items():
+        out['D4.' + k] = A(v)
+    for k, v in G_ema.state_dict().items():
+        out['E4.' + k] = A(v)
+    out['traj.steps'] = np.array(steps)
+    np.savez_compressed(os.path.join(HERE, 'pl.npz'), **out)
+    print('pl.npz', len(out))
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'pl':       # only the file added last (the others are unchanged)
+        gen_pl()
+        sys.exit(0)
     gen_ops()
     gen_modules()
     gen_model()
-    for f in ('ops.npz', 'modules.npz', 'model.npz'):
+    gen_pl()
+    for f in ('ops.npz', 'modules.npz', 'model.npz', 'pl.npz'):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, 'KiB')

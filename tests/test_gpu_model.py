@@ -146,9 +146,90 @@ def test_cuda_graph_trainer_matches_schedule_and_trains():
         assert torch.isfinite(d_loss) and torch.isfinite(g_loss) and torch.isfinite(fake).all(), it
         snaps.append(opt_d.flat_params.clone())
     assert kinds == [False, False, False, True, False, False, True, False, False, True]
-    assert set(gt.graphs) == {False, True}                      # both kinds were captured (2nd occurrence) ...
+    assert set(gt.graphs) == {(False, False), (True, False)}                      # both kinds were captured (2nd occurrence) ...
     assert gt.t.batches_done == 10
     for a, b in zip(snaps[:-1], snaps[1:]):
         assert not torch.equal(a, b)                            # ... and every replay really stepped the optimizer
     steps = opt_d._steps.cpu()
     assert int(steps.max()) == 10 and int(steps.min()) >= 7     # tensors without a gradient on the 3 R1 steps lag by 3
+
+
+def test_path_length_penalty_value_and_second_order_gradients(g_pl):
+    """a9: pl_penalty through the any-order modulated convolution vs the reference (value, per-sample norms via the
+    penalty, every parameter gradient -- second order through conv / up2x / bias_act w.r.t. the style)."""
+    from animeface_b200 import rng
+    from animeface_b200.ops.conv2d import any_order_modconv
+    from animeface_b200.train import pl_penalty
+    c, G, _ = _models(g_pl)
+    draws = [T(g_pl[f'eval.draw.{i}']) for i in range(int(g_pl['eval.n_draws']))]
+    with rng.replay(draws) as q:
+        with any_order_modconv():
+            image, style = G(T(g_pl['z']))
+        pl = pl_penalty(style, image, float(g_pl['pl_mean0']))
+        assert q.remaining == 0
+    _close(image, g_pl['eval.image'], BAR, 'image (any-order path)')
+    assert abs(float(pl) - float(g_pl['eval.pl'])) < BAR * abs(float(g_pl['eval.pl'])), (float(pl), float(g_pl['eval.pl']))
+    names = [n for n, _ in G.named_parameters()]
+    pg = torch.autograd.grad(pl, list(G.parameters()), allow_unused=True)
+    for n, gr in zip(names, pg):
+        if bool(g_pl['plnone.' + n]):
+            assert gr is None or float(gr.abs().max()) == 0, n
+        else:
+            _close(gr, g_pl['plgrad.' + n], BAR, 'plgrad.' + n)
+
+
+def test_any_order_modconv_matches_fused(g_pl):
+    """The composed (any-order) modulated convolution and the fused first-order ModConvFn give the same image and the
+    same first-order parameter gradients."""
+    from animeface_b200 import rng
+    from animeface_b200.ops.conv2d import any_order_modconv
+    c, G, _ = _models(g_pl)
+    z = T(g_pl['z'])
+    noises = [T(g_pl[f'eval.draw.{i}']) for i in range(int(g_pl['eval.n_draws']) - 1)]
+    with rng.replay(list(noises)):
+        a, _ = G(z)
+    with rng.replay(list(noises)), any_order_modconv():
+        b, _ = G(z)
+    _close(b, N(a), 1e-5, 'image')
+    w = torch.randn_like(a)
+    ga = torch.autograd.grad((a * w).sum(), list(G.parameters()), allow_unused=True)
+    gb = torch.autograd.grad((b * w).sum(), list(G.parameters()), allow_unused=True)
+    for (n, _), x, y in zip(G.named_parameters(), ga, gb):
+        assert (x is None) == (y is None), n
+        if x is not None:
+            _close(y, N(x), 1e-4, n)
+
+
+def test_four_step_trajectory_with_path_length(g_pl):
+    """Trainer.step x4 with pl_lambda > 0 (g_k=2: step 2 is a PL step; d_k=3: step 3 is an R1 step), reference draws."""
+    from animeface_b200 import rng
+    from animeface_b200.train import TrainConfig, Trainer, build_optimizers
+    from animeface_b200.model import Generator
+    c, G, D = _models(g_pl)
+    cfg = TrainConfig(image_size=c['image_size'], style_dim=c['style_dim'], channels=c['channels'], max_channels=c['max_channels'],
+                      block_num_conv=c['block_num_conv'], map_num_layers=c['map_num_layers'], mbsd_groups=c['mbsd_groups'],
+                      batch_size=c['batch'], lr=c['lr'], beta1=c['betas'][0], beta2=c['betas'][1], d_k=c['d_k'], g_k=c['g_k'],
+                      r1_lambda=c['r1_lambda'], pl_lambda=c['pl_lambda'])
+    G_ema = Generator(c['image_size'], c['image_channels'], c['style_dim'], c['channels'], c['max_channels'],
+                      c['block_num_conv'], c['map_num_layers'], True, 0.01).to(DEV)
+    G_ema.load_state_dict(G.state_dict())
+    opt_g, opt_d = build_optimizers(cfg, G, G_ema, D)
+    tr = Trainer(cfg, G, G_ema, D, opt_g, opt_d)
+    for it in range(int(g_pl['traj.steps'])):
+        draws = [T(g_pl[f'traj.{it}.draw.{i}']) for i in range(int(g_pl[f'traj.{it}.n_draws']))]
+        assert tr.is_pl_step() == (it == 2) and tr.is_r1_step() == (it == 3)
+        with rng.replay(draws) as q:
+            d_loss, g_loss, fake = tr.step(T(g_pl[f'traj.{it}.real']))
+            assert q.remaining == 0, 'draw order differs from the reference'
+        rd, rg = float(g_pl[f'traj.{it}.d_loss']), float(g_pl[f'traj.{it}.g_loss'])
+        assert abs(float(d_loss) - rd) < BAR * abs(rd), (it, float(d_loss), rd)
+        assert abs(float(g_loss) - rg) < BAR * abs(rg), (it, float(g_loss), rg)
+        rm = float(g_pl[f'traj.{it}.pl_mean'])
+        assert abs(float(tr.pl_mean) - rm) <= BAR * abs(rm) + 1e-12, (it, float(tr.pl_mean), rm)
+        _close(fake, g_pl[f'traj.{it}.fake'], 2 * BAR, f'fake.{it}')
+    for k, v in D.state_dict().items():
+        _close(v, g_pl['D4.' + k], 2 * BAR, 'D4.' + k)
+    for k, v in G.state_dict().items():
+        _close(v, g_pl['G4.' + k], 2 * BAR, 'G4.' + k)
+    for k, v in G_ema.state_dict().items():
+        _close(v, g_pl['E4.' + k], 2 * BAR, 'E4.' + k)

@@ -135,3 +135,55 @@ def test_training_trajectory(g_model):
         assert rel_err(v.detach().numpy(), g_model['D3.' + k]) < 1e-3 or np.abs(g_model['D3.' + k]).max() < 1e-6, k
     for k, v in sd_e.items():
         assert rel_err(v.detach().numpy(), g_model['E3.' + k]) < 1e-3 or np.abs(g_model['E3.' + k]).max() < 1e-6, k
+
+
+def test_path_length_penalty(g_pl):
+    """pl_penalty value, per-sample gradient norms and every second-order parameter gradient vs the reference."""
+    sd_g = _sd(g_pl, 'G0.', True)
+    for k in sd_g:
+        if k.endswith('.kernel'):
+            sd_g[k].requires_grad_(False)
+    draws = T.Draws([torch.from_numpy(g_pl[f'eval.draw.{i}']) for i in range(int(g_pl['eval.n_draws']))])
+    rng = T.ReplayDraws(draws)
+    image, style = T.generator(sd_g, torch.from_numpy(g_pl['z']), rng)
+    assert rel_err(image.detach().numpy(), g_pl['eval.image']) < 1e-5
+    pl = T.pl_penalty(style, image, float(g_pl['pl_mean0']), rng)
+    assert draws.pos == len(draws.items)
+    assert abs(float(pl) - float(g_pl['eval.pl'])) < 1e-4 * abs(float(g_pl['eval.pl']))
+    names = [k for k, v in sd_g.items() if v.requires_grad]
+    grads = torch.autograd.grad(pl, [sd_g[k] for k in names], allow_unused=True)
+    for k, gr in zip(names, grads):
+        ref = g_pl['plgrad.' + k]
+        if gr is None:
+            assert bool(g_pl['plnone.' + k]) or np.abs(ref).max() == 0, k
+        else:
+            assert rel_err(gr.numpy(), ref) < 2e-4 or np.abs(ref).max() < 1e-12, k
+
+
+def test_training_trajectory_with_path_length(g_pl):
+    """4 optimizer steps with pl_lambda > 0 (step 2 a PL step, step 3 an R1 step), reference draws replayed."""
+    cfg = ast.literal_eval(str(g_pl['cfg']))
+    sd_g, sd_d = _sd(g_pl, 'G0.', True), _sd(g_pl, 'D0.', True)
+    for k in sd_g:
+        if k.endswith('.kernel'):
+            sd_g[k].requires_grad_(False)
+    sd_e = {k: v.detach().clone() for k, v in sd_g.items()}
+    scfg = T.StepConfig(latent_dim=cfg['style_dim'], r1_lambda=cfg['r1_lambda'], d_k=cfg['d_k'], g_k=cfg['g_k'],
+                        pl_lambda=cfg['pl_lambda'], mbsd_groups=cfg['mbsd_groups'], lr=cfg['lr'], betas=cfg['betas'])
+    g_lr, g_b, d_lr, d_b = T.adam_hparams(scfg)
+    opt_g = torch.optim.Adam([v for v in sd_g.values() if v.requires_grad], lr=g_lr, betas=g_b)
+    opt_d = torch.optim.Adam(list(sd_d.values()), lr=d_lr, betas=d_b)
+    state = dict(pl_mean=0.)
+    for it in range(int(g_pl['traj.steps'])):
+        draws = T.Draws([torch.from_numpy(g_pl[f'traj.{it}.draw.{i}']) for i in range(int(g_pl[f'traj.{it}.n_draws']))])
+        real = torch.from_numpy(g_pl[f'traj.{it}.real'])
+        d_loss, g_loss, fake = T.train_step(sd_g, sd_d, sd_e, opt_g, opt_d, real, it, T.ReplayDraws(draws), scfg, state)
+        assert draws.pos == len(draws.items)
+        assert abs(float(d_loss) - float(g_pl[f'traj.{it}.d_loss'])) <= 2e-4 * abs(float(g_pl[f'traj.{it}.d_loss'])), it
+        assert abs(float(g_loss) - float(g_pl[f'traj.{it}.g_loss'])) <= 2e-4 * abs(float(g_pl[f'traj.{it}.g_loss'])), it
+        assert abs(state['pl_mean'] - float(g_pl[f'traj.{it}.pl_mean'])) <= 2e-4 * abs(float(g_pl[f'traj.{it}.pl_mean'])) + 1e-12, it
+        assert rel_err(fake.numpy(), g_pl[f'traj.{it}.fake']) < 1e-3, it
+    for k, v in sd_g.items():
+        assert rel_err(v.detach().numpy(), g_pl['G4.' + k]) < 1e-3 or np.abs(g_pl['G4.' + k]).max() < 1e-6, k
+    for k, v in sd_e.items():
+        assert rel_err(v.detach().numpy(), g_pl['E4.' + k]) < 1e-3 or np.abs(g_pl['E4.' + k]).max() < 1e-6, k
