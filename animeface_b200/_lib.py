@@ -27,6 +27,7 @@ SIGNATURES = {
     'sg2_version': (_int, []),
     'sg2_last_error': (C.c_char_p, []),
     'sg2_launch_count': (_i64, []),
+    'sg2_debug_trace': (_int, [_vp]),
     'sg2_upfirdn2d': (_int, [_vp, _vp, _vp, _int, _int, _int, _int, _int, _i64p, _int, _int, _i64p,
                              _int, _int, _int, _int, _int, _int, _int, _int, _int, _int, _int, _f, _vp]),
     'sg2_up2x_fwd': (_int, [_vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _vp]),

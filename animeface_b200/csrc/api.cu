@@ -5,6 +5,7 @@
 namespace sg2 {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+long long* g_trace = nullptr;
 
 // impl codes: 0 auto, 1 fp32 SIMT, 2 tcgen05 bf16x3 (per-tap loads), 3 tcgen05 tf32x3+promotion (per-tap loads),
 // 4 tcgen05 bf16x3 halo kernel, 5 tcgen05 tf32x3+promotion halo kernel.  `precise` steers auto towards 3/5.
@@ -25,6 +26,7 @@ using namespace sg2;
 extern "C" int sg2_version(void) { return 100; }
 extern "C" const char* sg2_last_error(void) { return g_err; }
 extern "C" int64_t sg2_launch_count(void) { return (int64_t)g_launches.load(); }
+extern "C" int sg2_debug_trace(void* device_buf) { g_trace = (long long*)device_buf; return SG2_OK; }
 
 // The packed buffer always starts with a 16-byte header {impl, transpose, co, ci} so a mismatched
 // pack/conv pair is caught instead of silently computing garbage.

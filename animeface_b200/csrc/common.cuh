@@ -12,6 +12,7 @@ namespace sg2 {
 
 extern thread_local char g_err[512];
 extern std::atomic<long long> g_launches;
+extern long long* g_trace;          // sg2_debug_trace buffer (device pointer) or null
 
 inline int fail(int code, const char* fmt, ...) {
     va_list ap;

@@ -18,6 +18,7 @@
 //                  (fp16 range: operands saturate at +-65504; forward activations and weights of this path are O(1))
 // Persistent CTAs (one per SM), double-buffered planes and TMEM accumulators, dedicated epilogue warps.
 // Warp roles: 0 patch TMA, 1 MMA (+TMEM alloc), 2..9 transform, 10.. epilogue/promotion, last = weight TMA.
+#include <stdlib.h>
 #include "tc_common.cuh"
 #include "conv.h"
 
@@ -44,7 +45,10 @@ template <int BN, bool PRECISE> struct Cfg {
     static constexpr int BTILE = 2 * BN * 128;                     // two planes of [BN rows x 128 B]
     static constexpr int SMEM = 1024 + SLOTS * SLOT_BYTES + 2 * 2 * PLANE_PITCH + BSTAGES * BTILE + 256;
     static constexpr int ACC_COLS = PRECISE ? 2 * BN : BN;         // one accumulator buffer (PRECISE: D1 | D2)
-    static constexpr uint32_t TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
+    // accumulator buffers: as many as TMEM's 512 columns hold, at most 4 -- the promotion / epilogue latency of a segment
+    // hides behind NACC - 1 segments of MMA work
+    static constexpr int NACC = 512 / ACC_COLS >= 4 ? 4 : 512 / ACC_COLS;
+    static constexpr uint32_t TMEM_COLS = NACC * ACC_COLS < 32 ? 32 : NACC * ACC_COLS;
 };
 
 struct Params {
@@ -57,6 +61,8 @@ struct Params {
     int nkb;                 // channel blocks
     int act;
     float alpha, gain;
+    long long* trace;        // sg2_debug_trace buffer or null
+    int promo_taps;          // PRECISE: taps accumulated in TMEM between two promotions (4 chained big*big MMAs per tap)
 };
 
 // non-swizzled K-major descriptor: LBO between 16-byte K chunks, SBO between 8-row groups, 16 B between rows
@@ -79,12 +85,16 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
     auto pl_empty = [&](int b) { return bar_base + 48u + 8u * b; };           // 2
     auto b_full = [&](int s) { return bar_base + 64u + 8u * s; };             // 3
     auto b_empty = [&](int s) { return bar_base + 88u + 8u * s; };            // 3
-    auto acc_full = [&](int b) { return bar_base + 112u + 8u * b; };          // 2
-    auto acc_empty = [&](int b) { return bar_base + 128u + 8u * b; };         // 2
-    const uint32_t tmem_slot = bar_base + 144u;
+    auto acc_full = [&](int b) { return bar_base + 112u + 8u * b; };          // NACC <= 4
+    auto acc_empty = [&](int b) { return bar_base + 144u + 8u * b; };         // NACC <= 4
+    const uint32_t tmem_slot = bar_base + 176u;
     auto plane = [&](int buf, int pl) { return plane_base + (uint32_t)((buf * 2 + pl) * PLANE_PITCH); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool tr = p.trace != nullptr;
+    long long* trow = p.trace + (size_t)blockIdx.x * 16;
+    const long long t_begin = tr ? clock64() : 0;
+    long long w0 = 0, w1 = 0, w2 = 0;            // wait-cycle accumulators of this thread's role
     const int pad = p.k >> 1, taps = p.k * p.k;
     const int PW = TW + 2 * pad, PH = TH + 2 * pad, PR = PW * PH;
     const uint32_t LBO = (uint32_t)PR * 16u, SBO = (uint32_t)PW * 16u;
@@ -101,8 +111,8 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
         for (int s = 0; s < 2; ++s) {
             mbar_init(st_full(s), 1); mbar_init(st_empty(s), 8);
             mbar_init(pl_full(s), 8); mbar_init(pl_empty(s), 1);
-            mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), C::EPI_WARPS);
         }
+        for (int s = 0; s < C::NACC; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), C::EPI_WARPS); }
         for (int s = 0; s < BSTAGES; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
         fence_barrier_init();
     }
@@ -115,7 +125,7 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
 
     if (warp == 0) {
         // ================= patch producer: one TMA box per (tile, channel block, 32-channel half) =================
-        if (lane == 0) {
+        if (elect_one()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
             int bx = 0;                                   // global box counter
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -124,48 +134,51 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
                 for (int kb = 0; kb < p.nkb; ++kb)
                     for (int hb = 0; hb < C::BOXES; ++hb, ++bx) {
                         const int s = bx % C::SLOTS;
-                        mbar_wait(st_empty(s), ((bx / C::SLOTS) & 1) ^ 1);
+                        mbar_wait_t(st_empty(s), ((bx / C::SLOTS) & 1) ^ 1, tr, w0);
                         mbar_expect_tx(st_full(s), (uint32_t)PR * 128u);
                         tma_load_4d(slot_base + s * SLOT_BYTES, &xmap, st_full(s), kb * C::KB + 32 * hb, x0 - pad, y0 - pad, b0);
                     }
             }
+            if (tr) trow[0] = w0;
         }
     } else if (warp == C::BWARP) {
         // ================= weight producer: one pre-packed tile per (tile, channel block, tap) =================
-        if (lane == 0) {
+        if (elect_one()) {
             int bt = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int nt = tile / p.m_tiles;
                 const unsigned char* wsrc = p.wp + (size_t)nt * p.nkb * taps * C::BTILE;
                 for (int i = 0; i < p.nkb * taps; ++i, ++bt) {
                     const int s = bt % BSTAGES;
-                    mbar_wait(b_empty(s), ((bt / BSTAGES) & 1) ^ 1);
+                    mbar_wait_t(b_empty(s), ((bt / BSTAGES) & 1) ^ 1, tr, w0);
                     mbar_expect_tx(b_full(s), C::BTILE);
                     bulk_load(b_base + s * C::BTILE, wsrc + (size_t)i * C::BTILE, C::BTILE, b_full(s));
                 }
             }
+            if (tr) trow[10] = w0;
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = PRECISE ? idesc_f16(BM, BN) : idesc_bf16(BM, BN);
             int bt = 0, kbg = 0, sg = 0;                  // global weight-tile / channel-block / accumulator-segment counters
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                int f = 0;                                // flat (kb, tap) index inside the tile
+                int f = 0, fseg = 0;                      // flat (kb, tap) index inside the tile / inside the accumulator segment
+                const int nflat = p.nkb * taps;
                 for (int kb = 0; kb < p.nkb; ++kb, ++kbg) {
                     const int pbuf = kbg & 1;
-                    mbar_wait(pl_full(pbuf), (kbg >> 1) & 1);
-                    for (int t = 0; t < taps; ++t, ++bt, ++f) {
+                    mbar_wait_t(pl_full(pbuf), (kbg >> 1) & 1, tr, w0);
+                    for (int t = 0, dy = 0, dx = 0; t < taps; ++t, ++bt, ++f, dx = (dx + 1 == p.k ? 0 : dx + 1), dy += (dx == 0)) {
                         // accumulator segment: PRECISE -> every 2 taps, else the whole tile
-                        const bool seg_start = PRECISE ? ((f & 1) == 0) : (f == 0);
-                        const bool seg_end = PRECISE ? ((f & 1) == 1 || f == p.nkb * taps - 1) : (f == p.nkb * taps - 1);
-                        const int abuf = sg & 1;
-                        if (seg_start) mbar_wait(acc_empty(abuf), ((sg >> 1) & 1) ^ 1);
+                        const bool seg_start = PRECISE ? (fseg == 0) : (f == 0);
+                        const bool seg_end = PRECISE ? (fseg == p.promo_taps - 1 || f == nflat - 1) : (f == nflat - 1);
+                        fseg = seg_end ? 0 : fseg + 1;
+                        const int abuf = sg % C::NACC;
+                        if (seg_start) mbar_wait_t(acc_empty(abuf), ((sg / C::NACC) & 1) ^ 1, tr, w2);
                         const int s = bt % BSTAGES;
-                        mbar_wait(b_full(s), (bt / BSTAGES) & 1);
+                        mbar_wait_t(b_full(s), (bt / BSTAGES) & 1, tr, w1);
                         tc_fence_after();
                         const uint32_t d = tmem_d + (uint32_t)(abuf * C::ACC_COLS);
-                        const int dy = t / p.k, dx = t % p.k;                      // already offset by +pad
                         const uint32_t arow = (uint32_t)(dy * PW + dx) * 16u;
                         const uint32_t a0 = plane(pbuf, 0) + arow, a1 = plane(pbuf, 1) + arow;
                         const uint32_t b0_ = b_base + s * C::BTILE, b1_ = b0_ + BN * 128;
@@ -188,6 +201,7 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
                     mma_commit(pl_empty(pbuf));
                 }
             }
+            if (tr) { trow[4] = w0; trow[5] = w1; trow[6] = w2; trow[7] = clock64() - t_begin; }
         }
     } else if (warp < 10) {
         // ================= transform: fp32 box -> split planes (non-swizzled K-major) =================
@@ -202,8 +216,8 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
                 bool waited = false;
                 for (int hb = 0; hb < C::BOXES; ++hb, ++bx) {
                     const int s = bx % C::SLOTS;
-                    mbar_wait(st_full(s), (bx / C::SLOTS) & 1);
-                    if (!waited) { mbar_wait(pl_empty(pbuf), ((kbg >> 1) & 1) ^ 1); waited = true; }
+                    mbar_wait_t(st_full(s), (bx / C::SLOTS) & 1, tr, w0);
+                    if (!waited) { mbar_wait_t(pl_empty(pbuf), ((kbg >> 1) & 1) ^ 1, tr, w1); waited = true; }
                     const uint32_t src0 = slot_base + s * SLOT_BYTES;
                     const int cbase = kb * C::KB + 32 * hb;                      // first channel of this box
                     // items = (row, 16-channel half); consecutive lanes take consecutive rows -> conflict-free both ways
@@ -250,6 +264,7 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
                 if (lane == 0) mbar_arrive(pl_full(pbuf));
             }
         }
+        if (tr && tt == 0) { trow[1] = w0; trow[2] = w1; trow[3] = clock64() - t_begin; }
     } else {
         // ================= epilogue warps (PRECISE: promotion of every segment, then epilogue) =================
         const int ew = warp - 10;
@@ -258,7 +273,7 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
         constexpr int COLS = PRECISE ? BN / 2 : BN;        // columns this thread owns
         const int cstart = PRECISE ? (ew >> 2) * COLS : 0;
         const int nflat = p.nkb * taps;
-        const int nseg = PRECISE ? (nflat + 1) / 2 : 1;
+        const int nseg = PRECISE ? (nflat + p.promo_taps - 1) / p.promo_taps : 1;
         int sg = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             int x0, y0, b0, n0;
@@ -267,68 +282,89 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
             const long long pix = ((long long)b0 * p.h + ey) * p.w + ex;
             const float nz = p.noise ? __ldg(p.noise + pix) : 0.f;
             float* yrow = p.y + (long long)b0 * p.ys[0] + (long long)ey * p.ys[2] + (long long)ex * p.ys[3];
-            float racc[PRECISE ? COLS : 1];
+            const float* osc = p.out_scale ? p.out_scale + (long long)b0 * p.co + n0 + cstart : nullptr;
+            const float* bsp = p.bias ? p.bias + n0 + cstart : nullptr;
+            auto finish4 = [&](float (&o)[4], int cbase) {          // out_scale, bias, noise, activation, gain on 4 channels
+                if (osc) { const float4 t = ldg4(osc + cbase); o[0] *= t.x; o[1] *= t.y; o[2] *= t.z; o[3] *= t.w; }
+                if (bsp) { const float4 t = ldg4(bsp + cbase); o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w; }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float val = o[e] + nz;
+                    if (p.act == 3) val = val > 0.f ? val : val * p.alpha;
+                    o[e] = val * p.gain;
+                }
+                const int cb = n0 + cstart + cbase;
+                if (p.ys[1] == 1) st4(yrow + cb, make_float4(o[0], o[1], o[2], o[3]));
+                else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) yrow[(long long)(cb + e) * p.ys[1]] = o[e];
+                }
+            };
             if (PRECISE) {
+                // every segment (the last one included) is promoted into fp32 registers and its TMEM buffer handed back at
+                // once; the epilogue then runs from registers while the MMA warp is already filling the next tile's segments
+                float racc[COLS];
 #pragma unroll
                 for (int j = 0; j < COLS; ++j) racc[j] = 0.f;
-                for (int seg = 0; seg < nseg - 1; ++seg, ++sg) {
-                    const int abuf = sg & 1;
-                    mbar_wait(acc_full(abuf), (sg >> 1) & 1);
+                for (int seg = 0; seg < nseg; ++seg, ++sg) {
+                    const int abuf = sg % C::NACC;
+                    mbar_wait_t(acc_full(abuf), (sg / C::NACC) & 1, tr, w0);
                     tc_fence_after();
+                    // G 16-column groups per round: 2G TMEM loads in flight, one wait
+                    constexpr int G = COLS == 32 ? 2 : 1;      // (64 columns per thread: the accumulators alone take 64 registers)
 #pragma unroll
-                    for (int c = 0; c < COLS / 16; ++c) {
-                        uint32_t v[16], v2[16];
-                        const uint32_t col = (uint32_t)(abuf * C::ACC_COLS + cstart + c * 16);
-                        tmem_ld16(tmem_d + ((uint32_t)(q4 * 32) << 16) + col, v);
-                        tmem_ld16(tmem_d + ((uint32_t)(q4 * 32) << 16) + col + BN, v2);
+                    for (int c = 0; c < COLS / 16; c += G) {
+                        uint32_t v[G][16], v2[G][16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) racc[c * 16 + j] += fmaf(__uint_as_float(v2[j]), 1.f / 2048.f, __uint_as_float(v[j]));
+                        for (int g = 0; g < G; ++g) {
+                            const uint32_t col = (uint32_t)(abuf * C::ACC_COLS + cstart + (c + g) * 16);
+                            tmem_ld16_async(tmem_d + ((uint32_t)(q4 * 32) << 16) + col, v[g]);
+                            tmem_ld16_async(tmem_d + ((uint32_t)(q4 * 32) << 16) + col + BN, v2[g]);
+                        }
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int g = 0; g < G; ++g) {
+                            reg_fence(v[g]); reg_fence(v2[g]);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                racc[(c + g) * 16 + j] += fmaf(__uint_as_float(v2[g][j]), 1.f / 2048.f, __uint_as_float(v[g][j]));
+                        }
                     }
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acc_empty(abuf));
                 }
-            }
-            // last (or only) segment: read, finish, store
-            const int abuf = sg & 1;
-            mbar_wait(acc_full(abuf), (sg >> 1) & 1);
-            tc_fence_after();
+#pragma unroll
+                for (int j = 0; j < COLS; j += 4) {
+                    float o[4] = {racc[j], racc[j + 1], racc[j + 2], racc[j + 3]};
+                    finish4(o, j);
+                }
+            } else {
+                // one segment per tile: read, finish, store, hand the buffer back
+                const int abuf = sg % C::NACC;
+                mbar_wait_t(acc_full(abuf), (sg / C::NACC) & 1, tr, w0);
+                tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < COLS / 16; ++c) {
-                uint32_t v[16], v2[16];
-                const uint32_t col = (uint32_t)(abuf * C::ACC_COLS + cstart + c * 16);
-                tmem_ld16(tmem_d + ((uint32_t)(q4 * 32) << 16) + col, v);
-                if (PRECISE) tmem_ld16(tmem_d + ((uint32_t)(q4 * 32) << 16) + col + BN, v2);
+                for (int c = 0; c < COLS / 16; ++c) {
+                    uint32_t v[16];
+                    tmem_ld16(tmem_d + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(abuf * C::ACC_COLS + cstart + c * 16), v);
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    float o[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int co = n0 + cstart + c * 16 + j + e;
-                        float val = __uint_as_float(v[j + e]);
-                        if (PRECISE) val += fmaf(__uint_as_float(v2[j + e]), 1.f / 2048.f, racc[(PRECISE ? c * 16 + j + e : 0)]);
-                        if (p.out_scale) val *= __ldg(p.out_scale + (long long)b0 * p.co + co);
-                        if (p.bias) val += __ldg(p.bias + co);
-                        val += nz;
-                        if (p.act == 3) val = val > 0.f ? val : val * p.alpha;
-                        o[e] = val * p.gain;
-                    }
-                    const int cb = n0 + cstart + c * 16 + j;
-                    if (p.ys[1] == 1) st4(yrow + cb, make_float4(o[0], o[1], o[2], o[3]));
-                    else {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) yrow[(long long)(cb + e) * p.ys[1]] = o[e];
+                    for (int j = 0; j < 16; j += 4) {
+                        float o[4] = {__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])};
+                        finish4(o, c * 16 + j);
                     }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty(abuf));
+                ++sg;
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty(abuf));
-            ++sg;
         }
+        if (tr && ew == 0 && lane == 0) { trow[8] = w0; trow[9] = clock64() - t_begin; }
     }
     tc_fence_before();
     __syncthreads();
+    if (tr && threadIdx.x == 0) { trow[11] = clock64() - t_begin; trow[12] = (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x; }
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_d, C::TMEM_COLS);
@@ -439,6 +475,18 @@ int conv_fwd_halo(const ConvParams& p, int precise, cudaStream_t st) {
     tp.n_tiles = p.co / bn;
     tp.nkb = (p.ci + 63) / 64;
     tp.act = p.act; tp.alpha = p.alpha; tp.gain = p.gain;
+    tp.trace = g_trace;
+    // promotion interval of the fp32-class kernel (taps accumulated in TMEM between two promotions, 4 chained big*big MMAs
+    // each).  Measured on B200 against fp64 (scripts/promo_sweep.py, profiles/r1b_promo_sweep.txt): 2 taps 3.5e-7,
+    // 5 taps 5e-7, 9 taps (one promotion per channel block) 0.8..1.1e-6 -- torch/cuDNN fp32 itself is 0.3..2e-6 on the
+    // same cases.  SG2_PROMO_TAPS overrides the default for that sweep.
+    static int promo_taps = 0;
+    if (!promo_taps) {
+        const char* e = getenv("SG2_PROMO_TAPS");
+        promo_taps = e ? atoi(e) : 2;
+        if (promo_taps < 1 || promo_taps > 9) promo_taps = 2;
+    }
+    tp.promo_taps = promo_taps;
     dim3 grid((unsigned)std::min(tp.m_tiles * tp.n_tiles, num_sms()));
     if (precise) {
         if (bn == 128) return halo::launch<128, true>(map, tp, grid, st);

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_fwd_tc_kernel(const __grid_c
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        if (elect_one()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
             int it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_fwd_tc_kernel(const __grid_c
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = idesc_bf16(BM, BN);
             int it = 0, ti = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_fwd_tc32_kernel(const __grid
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        if (elect_one()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
             int it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_fwd_tc32_kernel(const __grid
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = idesc_tf32(BM, BN);
             int it = 0, sg = 0;                      // global stage / segment counters (continue across tiles)
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {

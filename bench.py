@@ -238,7 +238,18 @@ def run_b200(args):
     e2e = dict(value=round(world * B * args.steps / (e2e_ms / 1e3), 2), unit='images/sec',
                h2d_bytes_per_step=B * 3 * 256 * 256 * 4, d2h_bytes_per_step=8)
 
+    def finish():
+        # Every rank leaves through here.  The CUDA graphs hold captured NCCL work, and tearing the process group down
+        # under them (or with a peer already gone) can block: synchronise, then exit without the teardown.
+        sys.stdout.flush()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            os._exit(0)
+
     if rank != 0:
+        finish()
         return
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -257,8 +268,7 @@ def run_b200(args):
                             model_tflops=round(value * FLOP_PER_IMG_STEP / 1e12, 2)),
                 clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu_baseline)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 def main():

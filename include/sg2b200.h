@@ -45,6 +45,10 @@ int         sg2_version(void);
 const char* sg2_last_error(void);
 /* number of kernels this library has launched in the calling process. */
 int64_t     sg2_launch_count(void);
+/* profiling aid (no reference counterpart): when `device_buf` is non-null the persistent tcgen05 convolution kernels
+ * add, per CTA, the cycles each warp role spent waiting on each pipeline barrier into device_buf[cta * 16 + slot]
+ * (int64, caller-zeroed, >= 16 * grid entries).  NULL switches it off (default). */
+int         sg2_debug_trace(void* device_buf);
 
 /* upfirdn2d ---------------------------------------------------------------- *
  * replaces: thirdparty/stylegan3_ops/ops/upfirdn2d.cpp:10  (pybind `upfirdn2d`)

@@ -301,7 +301,8 @@ def test_tcgen05_conv_variants_vs_fp64(impl, tol, n, ci, co, k, hw):
     assert rel_err(N(gx), N(ref_t)) < tol
 
 
-@pytest.mark.parametrize('n,ci,co,k,hw', [(8, 32, 64, 3, 16), (2, 64, 32, 3, 64), (8, 128, 128, 1, 16), (5, 96, 160, 3, 8), (8, 512, 512, 3, 4)])
+@pytest.mark.parametrize('n,ci,co,k,hw', [(8, 32, 64, 3, 16), (2, 64, 32, 3, 64), (8, 128, 128, 1, 16), (5, 96, 160, 3, 8), (8, 512, 512, 3, 4),
+                                          (3, 64, 64, 3, 32), (1, 32, 32, 3, 128), (2, 192, 96, 1, 32), (3, 64, 256, 3, 4)])
 def test_tcgen05_wgrad_vs_fp64(n, ci, co, k, hw):
     from animeface_b200.ops import conv2d as C
     import torch.nn.functional as F
