@@ -34,6 +34,10 @@ int conv_fwd_simt(const ConvParams& p, cudaStream_t st);
 int conv_wgrad_simt(WgradParams p, int accumulate, cudaStream_t st);
 int conv_pack_simt(const float* w, float* wp, int co, int ci, int k, float coef, int transpose, cudaStream_t st);
 
+// thin 1x1 layers, <= 4 channels on one side (conv_thin.cu); SG2_ENOTSUP when the shape / layout is not theirs
+int conv_fwd_thin(const ConvParams& p, cudaStream_t st);
+int conv_wgrad_thin(const WgradParams& p, cudaStream_t st);
+
 // tcgen05 path (conv_tc.cu)
 bool conv_tc_supported(int n, int h, int w, int ci, int co, int k);
 bool wgrad_tc_supported(int n, int h, int w, int ci, int co, int k);

@@ -279,6 +279,10 @@ __global__ void conv_pack_simt_kernel(const float* __restrict__ w, float* __rest
 }
 
 int conv_fwd_simt(const ConvParams& p, cudaStream_t st) {
+    {   // RGB-side 1x1 layers: one coalesced pass instead of a padded GEMM tile (conv_thin.cu)
+        const int rc = conv_fwd_thin(p, st);
+        if (rc != SG2_ENOTSUP) return rc;
+    }
     const long long P = (long long)p.n * p.h * p.w;
     const int mt = (int)ceil_div(P, kBM);
     if (p.co <= 32) {
@@ -300,6 +304,10 @@ int conv_wgrad_simt(WgradParams p, int accumulate, cudaStream_t st) {
     if (!accumulate) {
         cudaError_t e = cudaMemsetAsync(p.dw, 0, sizeof(float) * (size_t)p.co * p.ci * kk2, st);
         if (e != cudaSuccess) return fail(SG2_ELAUNCH, "conv_wgrad: memset: %s", cudaGetErrorString(e));
+    }
+    {
+        const int rc = conv_wgrad_thin(p, st);
+        if (rc != SG2_ENOTSUP) return rc;
     }
     const int mtiles = (p.ci + 63) / 64, ntiles = (p.co + 63) / 64;
     const long long tiles = (long long)mtiles * ntiles * kk2;

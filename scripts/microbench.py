@@ -83,6 +83,18 @@ def main():
         dst = torch.empty_like(g)
         report('torch copy_ (yardstick)', timeit(lambda: dst.copy_(g)), bytes_=g.numel() * 8)
         del gc, dst
+        # RGB-side 1x1 layers (conv_thin.cu): HBM streams over the wide tensor
+        rgb = torch.randn(B, 3, 256, 256, device=DEV)
+        wide = cl(B, 32, 256, 256)
+        w_in, w_out = torch.randn(32, 3, 1, 1, device=DEV), torch.randn(3, 32, 1, 1, device=DEV)
+        bb = torch.randn(32, device=DEV)
+        wb = wide.numel() * 4
+        report('from_rgb fwd 3->32@256 (+bias+lrelu)', timeit(lambda: C._conv_raw(rgb, w_in, 0.5, False, bias=bb, slope=0.2)), bytes_=wb + rgb.numel() * 4)
+        report('from_rgb wgrad 3->32@256', timeit(lambda: C._wgrad_raw(rgb, wide, 1, 0.5)), bytes_=wb + rgb.numel() * 4)
+        report('to_rgb fwd 32->3@256 (nchw out)', timeit(lambda: C._conv_raw(wide, w_out, 0.5, False, out_nchw=True)), bytes_=wb + rgb.numel() * 4)
+        report('to_rgb dgrad 3->32@256', timeit(lambda: C._conv_raw(rgb, w_out, 0.5, True)), bytes_=wb + rgb.numel() * 4)
+        report('to_rgb wgrad 32->3@256', timeit(lambda: C._wgrad_raw(wide, rgb, 1, 0.5)), bytes_=wb + rgb.numel() * 4)
+        del rgb, wide
         # convolution layers of the path (fwd / dgrad / wgrad), impl auto
         layers = [(32, 64, 256), (64, 64, 256), (64, 128, 128), (128, 128, 128), (256, 256, 64), (512, 512, 32), (512, 512, 16), (512, 512, 4)]
         if quick:

@@ -237,6 +237,40 @@ def test_conv_family_vs_torch(ci, co, k, hw):
     assert rel_err(N(gx), N(rx)) < 1e-4 and rel_err(N(gw), N(rw)) < 1e-4
 
 
+@pytest.mark.parametrize('n,ci,co,hw', [(5, 3, 32, 24), (2, 3, 64, 8), (3, 32, 3, 20), (4, 512, 3, 4), (2, 128, 3, 16), (3, 4, 8, 6), (2, 64, 1, 8)])
+def test_thin_1x1_convs_vs_fp64(n, ci, co, hw):
+    """RGB-side 1x1 layers (conv_thin.cu): fused forward incl. style / demod scales, bias, noise, lrelu and NCHW output,
+    data gradient (the transposed layer is thin on the other side) and weight gradient with per-sample scales."""
+    from animeface_b200.ops import conv2d as C
+    import torch.nn.functional as F
+    g = torch.Generator(device=DEV).manual_seed(ci * 7 + co)
+    x = torch.randn(n, ci, hw, hw + 2, device=DEV, generator=g)
+    w = torch.randn(co, ci, 1, 1, device=DEV, generator=g)
+    s = torch.randn(n, ci, device=DEV, generator=g)
+    d = torch.rand(n, co, device=DEV, generator=g) + 0.5
+    b = torch.randn(co, device=DEV, generator=g)
+    nz = torch.randn(n, 1, hw, hw + 2, device=DEV, generator=g)
+    gy = torch.randn(n, co, hw, hw + 2, device=DEV, generator=g)
+    coef = 0.11
+    ref = F.leaky_relu(F.conv2d((x * s[:, :, None, None]).double(), (w * coef).double()) * d[:, :, None, None].double()
+                       + b[None, :, None, None].double() + nz.double(), 0.2)
+    for nchw in (False, True):
+        y = C._conv_raw(x, w, coef, False, in_scale=s, out_scale=d, bias=b, noise=nz, slope=0.2, impl=1, out_nchw=nchw)
+        assert rel_err(N(y), N(ref)) < 2e-6
+    y0 = C._conv_raw(x, w, coef, False, impl=1)
+    assert rel_err(N(y0), N(F.conv2d(x.double(), (w * coef).double()))) < 2e-6
+    gx = C._conv_raw(gy, w, coef, True, impl=1)
+    assert rel_err(N(gx), N(F.conv_transpose2d(gy.double(), (w * coef).double()))) < 2e-6
+    wd = torch.zeros(co, ci, 1, 1, device=DEV, dtype=torch.float64, requires_grad=True)
+    yr = F.conv2d((x * s[:, :, None, None]).double(), wd * coef) * d[:, :, None, None].double()
+    ref_w, = torch.autograd.grad(yr, wd, gy.double())
+    dw = C._wgrad_raw(x, gy, 1, coef, in_scale=s, out_scale=d, impl=1)
+    assert rel_err(N(dw), N(ref_w)) < 5e-6
+    dw0 = C._wgrad_raw(x, gy, 1, coef, impl=1)
+    ref_w0, = torch.autograd.grad(F.conv2d(x.double(), wd * coef), wd, gy.double())
+    assert rel_err(N(dw0), N(ref_w0)) < 5e-6
+
+
 def test_conv_linearity_full_size():
     """Full-size (D block 1, conv2: 64->64 @256^2, B=32 would be 537 MB/tensor; B=8 keeps it quick):
     conv(a x1 + b x2) == a conv(x1) + b conv(x2), and the kernel is deterministic."""
