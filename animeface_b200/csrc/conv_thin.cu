@@ -6,7 +6,8 @@
 // kernel (conv_simt.cu pads K = 3 to 16 or N = 3 to 32) spends its time on zeros.  Here every kernel makes exactly one
 // coalesced pass over the wide tensor:
 //   thin_in_kernel    y[pix, co]   = act(os * sum_{c<CIN} x[pix,c] is[c] W[c,co] + bias + noise)     CIN <= 4, co % 4 == 0
-//   thin_out_kernel   y[pix, o<=4] = act(os * sum_c x[pix,c] is[c] W[c,o] + bias + noise)            ci % 4 == 0
+//   thin_out_kernel   y[pix, o<=4] = act(os * sum_{tap,c} x[pix+tap,c] is[c] W[tap,c,o] + bias + noise)  ci % 4 == 0, k = 1 | 3
+//                     (k = 3: the data gradient of the minibatch-stddev channel, 512 -> 1 @4^2, model.py:388-389)
 //   thin_wgrad_kernel R[C, T<=4]   = sum_pix wide[pix,C] * thin[pix,T]  (per-sample scales applied per block)
 // Weights arrive in the SIMT pack layout [cin][cout] (k = 1) of conv_pack_simt_kernel.  Algorithmic bytes = the wide
 // tensor once (+ the thin one), the HBM roofline of DESIGN.md section 3.
@@ -16,7 +17,7 @@
 namespace sg2 {
 namespace thin {
 
-constexpr int kMaxW = 4 * 512;            // floats of weight kept in shared memory (<= 4 x 512 channels)
+constexpr int kMaxW = 9 * 512;            // floats of weight kept in shared memory (k*k * thin * wide channels)
 
 // ---------------------------------------------------------------------------------------------------------------
 template <int CIN>
@@ -52,10 +53,11 @@ __global__ void __launch_bounds__(256) thin_in_kernel(ConvParams p) {
 // LANES lanes share one pixel: each takes the channel quads l, l + LANES, ...; partial dot products meet in a shuffle tree.
 template <int COUT, int LANES>
 __global__ void __launch_bounds__(256) thin_out_kernel(ConvParams p) {
-    __shared__ __align__(16) float sw[kMaxW];                      // transposed to [COUT][ci] for float4 reads
-    for (int i = threadIdx.x; i < COUT * p.ci; i += blockDim.x) {
-        const int o = i / p.ci, c = i % p.ci;
-        sw[i] = ((const float*)p.wp)[c * COUT + o];
+    __shared__ __align__(16) float sw[kMaxW];                      // transposed to [tap][COUT][ci] for float4 reads
+    const int taps = p.k * p.k, pad = p.k >> 1;
+    for (int i = threadIdx.x; i < taps * COUT * p.ci; i += blockDim.x) {
+        const int c = i % p.ci, o = (i / p.ci) % COUT, t = i / (p.ci * COUT);
+        sw[i] = ((const float*)p.wp)[((long long)t * p.ci + c) * COUT + o];
     }
     __syncthreads();
     const int hw = p.h * p.w, cq = p.ci >> 2;
@@ -66,18 +68,23 @@ __global__ void __launch_bounds__(256) thin_out_kernel(ConvParams p) {
     for (long long pix0 = slot; pix0 < (P + nslots - 1) / nslots * nslots; pix0 += nslots) {   // uniform trip count per warp
         const bool ok = pix0 < P;
         const long long pix = ok ? pix0 : P - 1;
-        const int b = (int)(pix / hw);
+        const int b = (int)(pix / hw), r = (int)(pix % hw), oy = r / p.w, ox = r % p.w;
         float acc[COUT];
 #pragma unroll
         for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
-        const float* xp = p.x + pix * p.ci;
-        for (int q = lane; q < cq; q += LANES) {
-            float4 xv = ldg4(xp + 4 * q);
-            if (p.in_scale) xv = mul4(xv, ldg4(p.in_scale + (long long)b * p.ci + 4 * q));
+        for (int t = 0; t < taps; ++t) {
+            const int iy = oy + t / p.k - pad, ix = ox + t % p.k - pad;
+            if (iy < 0 || iy >= p.h || ix < 0 || ix >= p.w) continue;           // zero padding
+            const float* xp = p.x + (((long long)b * p.h + iy) * p.w + ix) * p.ci;
+            const float* wt = sw + t * COUT * p.ci;
+            for (int q = lane; q < cq; q += LANES) {
+                float4 xv = ldg4(xp + 4 * q);
+                if (p.in_scale) xv = mul4(xv, ldg4(p.in_scale + (long long)b * p.ci + 4 * q));
 #pragma unroll
-            for (int o = 0; o < COUT; ++o) {
-                const float4 w4 = *reinterpret_cast<const float4*>(&sw[o * p.ci + 4 * q]);
-                acc[o] = fmaf(xv.x, w4.x, fmaf(xv.y, w4.y, fmaf(xv.z, w4.z, fmaf(xv.w, w4.w, acc[o]))));
+                for (int o = 0; o < COUT; ++o) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(&wt[o * p.ci + 4 * q]);
+                    acc[o] = fmaf(xv.x, w4.x, fmaf(xv.y, w4.y, fmaf(xv.z, w4.z, fmaf(xv.w, w4.w, acc[o]))));
+                }
             }
         }
 #pragma unroll
@@ -85,7 +92,6 @@ __global__ void __launch_bounds__(256) thin_out_kernel(ConvParams p) {
 #pragma unroll
             for (int o = 0; o < COUT; ++o) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], s);
         if (ok && lane == 0) {
-            const int r = (int)(pix % hw), oy = r / p.w, ox = r % p.w;
             const float nz = p.noise ? __ldg(p.noise + pix) : 0.f;
             float* yp = p.y + b * p.ys[0] + oy * p.ys[2] + ox * p.ys[3];
 #pragma unroll
@@ -166,11 +172,10 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(WgParams p) {
 // The launchers below are tried first by conv_fwd_simt / conv_wgrad_simt; they return SG2_ENOTSUP when the shape or
 // layout is not the thin one, and the generic fp32 kernels run instead.
 int conv_fwd_thin(const ConvParams& p, cudaStream_t st) {
-    if (p.k != 1) return SG2_ENOTSUP;
     const long long P = (long long)p.n * p.h * p.w;
     if (P > 2147483647LL / 4) return SG2_ENOTSUP;
     const bool y_dense_nhwc = p.ys[1] == 1 && p.ys[3] == p.co && p.ys[2] == (long long)p.w * p.co && p.ys[0] == (long long)p.h * p.w * p.co;
-    if (p.ci <= 4 && (p.co % 4) == 0 && p.ci * p.co <= thin::kMaxW && y_dense_nhwc && ((uintptr_t)p.y % 16) == 0) {
+    if (p.k == 1 && p.ci <= 4 && (p.co % 4) == 0 && p.ci * p.co <= thin::kMaxW && y_dense_nhwc && ((uintptr_t)p.y % 16) == 0) {
         const long long work = P * (p.co / 4);
         const int blocks = (int)std::min<long long>(ceil_div(work, 256), (long long)num_sms() * 16);
         switch (p.ci) {
@@ -181,7 +186,7 @@ int conv_fwd_thin(const ConvParams& p, cudaStream_t st) {
         }
         return launched("conv_thin_in");
     }
-    if (p.co <= 4 && (p.ci % 4) == 0 && p.ci * p.co <= thin::kMaxW && ((uintptr_t)p.x % 16) == 0) {
+    if (p.co <= 4 && (p.ci % 4) == 0 && p.k * p.k * p.ci * p.co <= thin::kMaxW && ((uintptr_t)p.x % 16) == 0) {
         const int cq = p.ci / 4;
         const int lanes = cq >= 32 ? 32 : (cq >= 16 ? 16 : (cq >= 8 ? 8 : 4));
         const int blocks = (int)std::min<long long>(ceil_div(P * lanes, 256), (long long)num_sms() * 16);

@@ -10,6 +10,7 @@
 //   * upfirdn2d_vec4_nhwc : fp32 channels_last, C % 4 == 0 -- one thread = one output pixel x 4
 //     channels, 128-bit coalesced loads/stores, taps served from L1, only non-zero phases visited.
 //   * upfirdn2d_generic<T>: any dtype / strides / factors, thread order follows y's memory order.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace sg2 {
@@ -157,6 +158,132 @@ __global__ void __launch_bounds__(256) upfirdn2d_strip_nhwc(UpfirdnParams p) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Register-ring fast path for up = 1 (FIR, optionally decimating) -- the blur in front of every discriminator
+// convolution of the StyleGAN3-style networks (conv2d_resample.py:101-108: [1,3,3,1] x [1,3,3,1], down 1 or 2).
+//   y[jy][jx] = sum_{a<FH} sum_{b<FW} wt[a][b] * x[jy*DOWN - pady0 + a][jx*DOWN - padx0 + b]      (zero outside)
+// A thread owns one output column (x 4 channels for NHWC, V = float4; one plane for NCHW, V = float) and walks down a
+// strip of STRIP output rows keeping the FH x FW input window in registers: going one row down costs DOWN x FW loads
+// instead of FH x FW -- each input element is fetched FW / DOWN times per thread-column instead of FH*FW / DOWN^2, and
+// neighbouring columns' fetches hit L1.  The strip loop is fully unrolled so the ring is addressed with constants.
+template <class V> struct RingVec;
+template <> struct RingVec<float4> {
+    static __device__ __forceinline__ float4 zero() { return f4zero(); }
+    static __device__ __forceinline__ float4 ld(const float* p) { return ldg4(p); }
+    static __device__ __forceinline__ void st(float* p, const float4& v) { st4_cs(p, v); }
+    static __device__ __forceinline__ void fma(float4& a, float s, const float4& v) { fma4(a, s, v); }
+};
+template <> struct RingVec<float> {
+    static __device__ __forceinline__ float zero() { return 0.f; }
+    static __device__ __forceinline__ float ld(const float* p) { return __ldg(p); }
+    static __device__ __forceinline__ void st(float* p, float v) { __stcs(p, v); }
+    static __device__ __forceinline__ void fma(float& a, float s, float v) { a = fmaf(s, v, a); }
+};
+
+template <class V, int FH, int FW, int DOWN, int COLS, int STRIP>
+__global__ void __launch_bounds__(256) upfirdn2d_ring_kernel(UpfirdnParams p) {
+    typedef RingVec<V> R;
+    constexpr bool NHWC = sizeof(V) == 16;
+    constexpr int WW = (COLS - 1) * DOWN + FW;     // input window width of the COLS adjacent outputs of a thread
+    // weights oriented like the generic kernels: wt[a][b] = f[flip ? a : FH-1-a][flip ? b : FW-1-b] * gain
+    float wt[FH][FW];
+#pragma unroll
+    for (int a = 0; a < FH; ++a)
+#pragma unroll
+        for (int b = 0; b < FW; ++b)
+            wt[a][b] = __ldg(p.f + (p.flip ? a : FH - 1 - a) * FW + (p.flip ? b : FW - 1 - b)) * p.gain;
+    int jx, img, strip = blockIdx.y;
+    const float* x; float* y;
+    int xrow, xcol, yrow, ycol;                    // element strides of one row / one column step
+    if (NHWC) {
+        const int cq = p.c >> 2, xs = 256 / cq;
+        const int q = threadIdx.x % cq;
+        jx = (blockIdx.x * xs + threadIdx.x / cq) * COLS;
+        img = blockIdx.z;
+        x = (const float*)p.x + (size_t)img * p.xs[0] + 4 * q;
+        y = (float*)p.y + (size_t)img * p.ys[0] + 4 * q;
+        xcol = p.c; ycol = p.c; xrow = p.in_w * p.c; yrow = p.out_w * p.c;
+    } else {
+        // one plane: work items (strip, column group) flattened so that a block is full whatever out_w is
+        const int ncols = (p.out_w + COLS - 1) / COLS;
+        const int item = blockIdx.x * 256 + threadIdx.x;
+        strip = item / ncols;
+        jx = (item - strip * ncols) * COLS;
+        img = blockIdx.z;                          // plane index n * C + c
+        x = (const float*)p.x + (size_t)img * p.in_h * p.in_w;
+        y = (float*)p.y + (size_t)img * p.out_h * p.out_w;
+        xcol = 1; ycol = 1; xrow = p.in_w; yrow = p.out_w;
+    }
+    if (jx >= p.out_w || strip * STRIP >= p.out_h) return;
+    const int jy0 = strip * STRIP;
+    const int ix0 = jx * DOWN - p.padx0, iy0 = jy0 * DOWN - p.pady0;
+    bool colok[WW];
+#pragma unroll
+    for (int b = 0; b < WW; ++b) colok[b] = (unsigned)(ix0 + b) < (unsigned)p.in_w;
+    const float* xc = x + (ptrdiff_t)ix0 * xcol;
+    V ring[FH][WW];
+    auto load_row = [&](int k, V (&dst)[WW]) {     // input row iy0 + k
+        const int iy = iy0 + k;
+        const bool rowok = (unsigned)iy < (unsigned)p.in_h;
+        const float* xr = xc + (ptrdiff_t)iy * xrow;
+#pragma unroll
+        for (int b = 0; b < WW; ++b) dst[b] = (rowok && colok[b]) ? R::ld(xr + (ptrdiff_t)b * xcol) : R::zero();
+    };
+#pragma unroll
+    for (int k = 0; k < FH - DOWN; ++k) load_row(k, ring[k % FH]);
+#pragma unroll
+    for (int s = 0; s < STRIP; ++s) {
+#pragma unroll
+        for (int k = FH - DOWN; k < FH; ++k) load_row(s * DOWN + k, ring[(s * DOWN + k) % FH]);
+#pragma unroll
+        for (int e = 0; e < COLS; ++e) {
+            V acc = R::zero();
+#pragma unroll
+            for (int a = 0; a < FH; ++a)
+#pragma unroll
+                for (int b = 0; b < FW; ++b) R::fma(acc, wt[a][b], ring[(s * DOWN + a) % FH][e * DOWN + b]);
+            if (jy0 + s < p.out_h && jx + e < p.out_w) R::st(y + (size_t)(jy0 + s) * yrow + (size_t)(jx + e) * ycol, acc);
+        }
+    }
+}
+
+template <class V, int FH, int FW, int DOWN, int COLS>
+static int launch_ring_cols(const UpfirdnParams& p, cudaStream_t st) {
+    constexpr int STRIP = 16;
+    constexpr bool NHWC = sizeof(V) == 16;
+    dim3 grid;
+    if (NHWC) grid = dim3((unsigned)ceil_div(p.out_w, 256 / (p.c / 4)), (unsigned)ceil_div(p.out_h, STRIP), (unsigned)p.n);
+    else grid = dim3((unsigned)ceil_div(ceil_div(p.out_w, COLS) * ceil_div(p.out_h, STRIP), 256), 1u, (unsigned)(p.n * p.c));
+    upfirdn2d_ring_kernel<V, FH, FW, DOWN, COLS, STRIP><<<grid, 256, 0, st>>>(p);
+    return launched("upfirdn2d_ring");
+}
+
+template <class V, int FH, int FW, int DOWN>
+static int launch_ring(const UpfirdnParams& p, cudaStream_t st) {
+    // NHWC: a thread = one pixel column x 4 channels.  NCHW: COLS adjacent columns of one plane.
+    if constexpr (sizeof(V) == 16) {
+        return launch_ring_cols<V, FH, FW, DOWN, 1>(p, st);
+    } else {
+        static int cols = 0;
+        if (!cols) { const char* e = getenv("SG2_UPF_COLS"); cols = e ? atoi(e) : 2; }     // measured on B200 (U4, NCHW): 1 -> 0.35, 2 -> 0.51, 4 -> 0.48 of HBM peak
+        if (cols == 4) return launch_ring_cols<V, FH, FW, DOWN, 4>(p, st);
+        if (cols == 2) return launch_ring_cols<V, FH, FW, DOWN, 2>(p, st);
+        return launch_ring_cols<V, FH, FW, DOWN, 1>(p, st);
+    }
+}
+
+// returns SG2_ENOTSUP when the call is not one of the ring shapes
+template <class V>
+static int try_ring(const UpfirdnParams& p, cudaStream_t st) {
+    if (p.upx != 1 || p.upy != 1 || p.downx != p.downy || p.fh != p.fw) return SG2_ENOTSUP;
+    if (p.fh == 4 && p.downx == 1) return launch_ring<V, 4, 4, 1>(p, st);
+    if (p.fh == 4 && p.downx == 2) return launch_ring<V, 4, 4, 2>(p, st);
+    if (p.fh == 3 && p.downx == 1) return launch_ring<V, 3, 3, 1>(p, st);
+    if (p.fh == 2 && p.downx == 2) return launch_ring<V, 2, 2, 2>(p, st);
+    return SG2_ENOTSUP;
+}
+
 }  // namespace sg2
 
 using namespace sg2;
@@ -205,6 +332,17 @@ extern "C" int sg2_upfirdn2d(const void* x, const float* f, void* y, int dtype,
                             p.ys[2] == (long long)out_w * c && (p.xs[0] % 4) == 0 && (p.ys[0] % 4) == 0 &&
                             ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0;
     const int cq = c / 4;
+    const bool nchw_dense = p.xs[3] == 1 && p.ys[3] == 1 && p.xs[2] == in_w && p.ys[2] == out_w &&
+                            p.xs[1] == (long long)in_h * in_w && p.ys[1] == (long long)out_h * out_w &&
+                            p.xs[0] == (long long)c * in_h * in_w && p.ys[0] == (long long)c * out_h * out_w;
+    if (dtype == SG2_F32 && nhwc_dense && cq <= 256 && (256 % cq) == 0 && n <= 65535) {
+        const int rc = try_ring<float4>(p, st);
+        if (rc != SG2_ENOTSUP) return rc;
+    }
+    if (dtype == SG2_F32 && nchw_dense && (long long)n * c <= 65535) {
+        const int rc = try_ring<float>(p, st);
+        if (rc != SG2_ENOTSUP) return rc;
+    }
     if (dtype == SG2_F32 && nhwc_dense && fh * fw <= kMaxTaps && cq <= 256 && (256 % cq) == 0 && n <= 65535) {
         const int xs = 256 / cq;
         dim3 grid((unsigned)ceil_div(out_w, xs), (unsigned)ceil_div(out_h, kUpfStrip), (unsigned)n);

@@ -54,6 +54,25 @@ def test_upfirdn2d_dtypes_and_big_nhwc():
                 assert rel_err(N(y), ref) < tol, (kw, dt, cl)
 
 
+def test_upfirdn2d_ring_path_variants():
+    """The register-ring fast path (up = 1; 4x4 / 3x3 / 2x2 taps; down 1 or 2) against the oracle: asymmetric and
+    negative padding, flipped non-symmetric filters, gains, ragged sizes, both layouts."""
+    from animeface_b200.ops import upfirdn2d as U
+    from oracle import ops_numpy as O
+    rs = np.random.RandomState(1)
+    x = rs.randn(3, 12, 37, 21).astype(np.float32)
+    cases = [(rs.randn(4, 4), dict(padding=[2, 1, 0, 3], gain=1.7)), (rs.randn(4, 4), dict(down=2, padding=[1, 2, 2, 1], flip_filter=True)),
+             (rs.randn(3, 3), dict(padding=[1, 1, 1, 1])), (rs.randn(3, 3), dict(padding=[-1, 2, 3, -2], flip_filter=True)),
+             (rs.randn(2, 2), dict(down=2)), (rs.randn(4, 4), dict(down=2, padding=[-2, 5, 4, -1]))]
+    for f, kw in cases:
+        f = f.astype(np.float32)
+        ref = O.upfirdn2d(x, f, **kw)
+        for cl in (False, True):
+            xt = T(x).contiguous(memory_format=torch.channels_last) if cl else T(x)
+            y = U.upfirdn2d(xt, T(f), **kw)
+            assert y.shape == ref.shape and rel_err(N(y), ref) < 1e-5, (f.shape, kw, cl)
+
+
 def test_upfirdn2d_errors():
     from animeface_b200.ops import upfirdn2d as U
     x = torch.zeros(1, 1, 4, 4, device=DEV)
@@ -269,6 +288,21 @@ def test_thin_1x1_convs_vs_fp64(n, ci, co, hw):
     dw0 = C._wgrad_raw(x, gy, 1, coef, impl=1)
     ref_w0, = torch.autograd.grad(F.conv2d(x.double(), wd * coef), wd, gy.double())
     assert rel_err(N(dw0), N(ref_w0)) < 5e-6
+
+
+@pytest.mark.parametrize('n,ci,co,hw', [(8, 512, 1, 4), (3, 64, 2, 9)])
+def test_thin_3x3_to_few_channels_vs_fp64(n, ci, co, hw):
+    """3x3 layer with <= 4 output channels (the data gradient of the minibatch-stddev channel is 512 -> 1 @4^2)."""
+    from animeface_b200.ops import conv2d as C
+    import torch.nn.functional as F
+    g = torch.Generator(device=DEV).manual_seed(ci + co)
+    x = torch.randn(n, ci, hw, hw, device=DEV, generator=g)
+    w = torch.randn(co, ci, 3, 3, device=DEV, generator=g)
+    y = C._conv_raw(x, w, 0.2, False, impl=1)
+    assert rel_err(N(y), N(F.conv2d(x.double(), (w * 0.2).double(), padding=1))) < 2e-6
+    wt = torch.randn(ci, co, 3, 3, device=DEV, generator=g)          # as a data gradient: gy has ci channels
+    gx = C._conv_raw(x, wt, 0.2, True, impl=1)
+    assert rel_err(N(gx), N(F.conv_transpose2d(x.double(), (wt * 0.2).double(), padding=1))) < 2e-6
 
 
 def test_conv_linearity_full_size():
