@@ -195,6 +195,28 @@ class DBlock(nn.Module):
         return avgpool2(x, t, 1.0 / math.sqrt(2.0))      # (down(x) + down(t)) / sqrt(2), one kernel
 
 
+_mbstd_chunks = 1
+
+
+class independent_batches:
+    """Context manager: the batch handed to the Discriminator is ``chunks`` independent mini-batches concatenated
+    (the training step runs D(real) and D(fake) of implementations/StyleGAN2/utils.py:65,69 as ONE call).  Every layer of D
+    is per-sample except MiniBatchStdDev, whose group statistics must not mix the mini-batches: inside this context it
+    evaluates each chunk on its own, exactly as the separate calls would."""
+
+    def __init__(self, chunks):
+        self.chunks = int(chunks)
+
+    def __enter__(self):
+        global _mbstd_chunks
+        self._prev, _mbstd_chunks = _mbstd_chunks, self.chunks
+        return self
+
+    def __exit__(self, *exc):
+        global _mbstd_chunks
+        _mbstd_chunks = self._prev
+
+
 class MiniBatchStdDev(nn.Module):
     def __init__(self, group_size, eps=1e-4):
         super().__init__()
@@ -202,6 +224,9 @@ class MiniBatchStdDev(nn.Module):
         self.eps = eps
 
     def forward(self, x):
+        if _mbstd_chunks > 1:
+            assert x.shape[0] % _mbstd_chunks == 0
+            return torch.cat([minibatch_stddev(c, self.group_size, self.eps) for c in x.chunk(_mbstd_chunks, dim=0)], dim=0)
         return minibatch_stddev(x, self.group_size, self.eps)
 
 

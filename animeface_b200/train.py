@@ -26,7 +26,7 @@ import torch
 from . import rng
 from .ops.conv2d import any_order_modconv
 from .diffaugment import DiffAugment
-from .model import Discriminator, Generator, init_weight_N01, supplied_noise  # noqa: F401
+from .model import Discriminator, Generator, independent_batches, init_weight_N01, supplied_noise  # noqa: F401
 from .nnutils import FlatAdam, update_ema
 from .nnutils.loss import NonSaturatingLoss, calc_grad, r1_regularizer
 
@@ -144,7 +144,11 @@ class Trainer:
             # values -- only their random draws (consumed above) matter for the stream.
             D_loss = self.r1(real, D, None) * cfg.r1_lambda * cfg.d_k
         else:
-            D_loss = self.loss.d_loss(D(real_aug), D(fake_aug))
+            # D(real_aug) and D(fake_aug) (utils.py:65,69) as one call over the concatenated batch: same per-sample
+            # results (minibatch-stddev is evaluated per half), half the launches and weight packs of the D phase
+            with independent_batches(2):
+                prob = D(torch.cat([real_aug, fake_aug], dim=0))
+            D_loss = self.loss.d_loss(prob[:B], prob[B:])
         D_loss.backward()
         self.opt_d.step()
         # ---- generator phase (utils.py:88-113)
