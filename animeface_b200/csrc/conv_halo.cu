@@ -44,11 +44,15 @@ template <int BN, bool PRECISE> struct Cfg {
     static constexpr int SLOTS = BN == 128 ? 1 : 2;                // staging slots (boxes in flight); 1 keeps BN=128 under 227 KB
     static constexpr int BTILE = 2 * BN * 128;                     // two planes of [BN rows x 128 B]
     static constexpr int SMEM = 1024 + SLOTS * SLOT_BYTES + 2 * 2 * PLANE_PITCH + BSTAGES * BTILE + 256;
-    static constexpr int ACC_COLS = PRECISE ? 2 * BN : BN;         // one accumulator buffer (PRECISE: D1 | D2)
-    // accumulator buffers: as many as TMEM's 512 columns hold, at most 4 -- the promotion / epilogue latency of a segment
-    // hides behind NACC - 1 segments of MMA work
-    static constexpr int NACC = 512 / ACC_COLS >= 4 ? 4 : 512 / ACC_COLS;
-    static constexpr uint32_t TMEM_COLS = NACC * ACC_COLS < 32 ? 32 : NACC * ACC_COLS;
+    // TMEM accumulators (BN fp32 columns each).  D1 buffers take the big*big products of one segment (promoted into
+    // registers and handed back segment by segment; the promotion latency hides behind ND1 - 1 segments of MMA work).
+    // PRECISE only: D2 buffers take the cross terms small*big + big*small of a WHOLE tile -- they are 2^-11 of the result,
+    // so the accumulator truncation that forces D1's short chains is irrelevant for them, and they are read once per tile.
+    static constexpr int ND2 = PRECISE ? (BN == 128 ? 1 : 2) : 0;
+    static constexpr int ND1 = PRECISE ? (BN == 128 ? 3 : 4) : 4;
+    static constexpr int D1_COL0 = ND2 * BN;                       // D2 buffers first, then the D1 buffers
+    static constexpr uint32_t TMEM_COLS = (ND1 + ND2) * BN <= 32 ? 32 : ((ND1 + ND2) * BN <= 64 ? 64 : ((ND1 + ND2) * BN <= 128 ? 128 :
+                                          ((ND1 + ND2) * BN <= 256 ? 256 : 512)));
 };
 
 struct Params {
@@ -85,9 +89,11 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
     auto pl_empty = [&](int b) { return bar_base + 48u + 8u * b; };           // 2
     auto b_full = [&](int s) { return bar_base + 64u + 8u * s; };             // 3
     auto b_empty = [&](int s) { return bar_base + 88u + 8u * s; };            // 3
-    auto acc_full = [&](int b) { return bar_base + 112u + 8u * b; };          // NACC <= 4
-    auto acc_empty = [&](int b) { return bar_base + 144u + 8u * b; };         // NACC <= 4
-    const uint32_t tmem_slot = bar_base + 176u;
+    auto acc_full = [&](int b) { return bar_base + 112u + 8u * b; };          // ND1 <= 4
+    auto acc_empty = [&](int b) { return bar_base + 144u + 8u * b; };         // ND1 <= 4
+    auto d2_full = [&](int b) { return bar_base + 176u + 8u * b; };           // ND2 <= 2
+    auto d2_empty = [&](int b) { return bar_base + 192u + 8u * b; };          // ND2 <= 2
+    const uint32_t tmem_slot = bar_base + 208u;
     auto plane = [&](int buf, int pl) { return plane_base + (uint32_t)((buf * 2 + pl) * PLANE_PITCH); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -112,7 +118,8 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
             mbar_init(st_full(s), 1); mbar_init(st_empty(s), 8);
             mbar_init(pl_full(s), 8); mbar_init(pl_empty(s), 1);
         }
-        for (int s = 0; s < C::NACC; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), C::EPI_WARPS); }
+        for (int s = 0; s < C::ND1; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), C::EPI_WARPS); }
+        for (int s = 0; s < C::ND2; ++s) { mbar_init(d2_full(s), 1); mbar_init(d2_empty(s), C::EPI_WARPS); }
         for (int s = 0; s < BSTAGES; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
         fence_barrier_init();
     }
@@ -161,8 +168,11 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
         // ================= MMA issuer =================
         if (elect_one()) {
             constexpr uint32_t idesc = PRECISE ? idesc_f16(BM, BN) : idesc_bf16(BM, BN);
-            int bt = 0, kbg = 0, sg = 0;                  // global weight-tile / channel-block / accumulator-segment counters
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int bt = 0, kbg = 0, sg = 0, ti = 0;          // global weight-tile / channel-block / accumulator-segment / tile counters
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+                const int d2buf = PRECISE ? ti % (C::ND2 ? C::ND2 : 1) : 0;
+                if (PRECISE) mbar_wait_t(d2_empty(d2buf), ((ti / (C::ND2 ? C::ND2 : 1)) & 1) ^ 1, tr, w2);
+                const uint32_t d2 = tmem_d + (uint32_t)(d2buf * BN);
                 int f = 0, fseg = 0;                      // flat (kb, tap) index inside the tile / inside the accumulator segment
                 const int nflat = p.nkb * taps;
                 for (int kb = 0; kb < p.nkb; ++kb, ++kbg) {
@@ -173,12 +183,12 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
                         const bool seg_start = PRECISE ? (fseg == 0) : (f == 0);
                         const bool seg_end = PRECISE ? (fseg == p.promo_taps - 1 || f == nflat - 1) : (f == nflat - 1);
                         fseg = seg_end ? 0 : fseg + 1;
-                        const int abuf = sg % C::NACC;
-                        if (seg_start) mbar_wait_t(acc_empty(abuf), ((sg / C::NACC) & 1) ^ 1, tr, w2);
+                        const int abuf = sg % C::ND1;
+                        if (seg_start) mbar_wait_t(acc_empty(abuf), ((sg / C::ND1) & 1) ^ 1, tr, w2);
                         const int s = bt % BSTAGES;
                         mbar_wait_t(b_full(s), (bt / BSTAGES) & 1, tr, w1);
                         tc_fence_after();
-                        const uint32_t d = tmem_d + (uint32_t)(abuf * C::ACC_COLS);
+                        const uint32_t d = tmem_d + (uint32_t)(C::D1_COL0 + abuf * BN);
                         const uint32_t arow = (uint32_t)(dy * PW + dx) * 16u;
                         const uint32_t a0 = plane(pbuf, 0) + arow, a1 = plane(pbuf, 1) + arow;
                         const uint32_t b0_ = b_base + s * C::BTILE, b1_ = b0_ + BN * 128;
@@ -188,15 +198,16 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
                             const uint64_t db0 = kmajor_desc(b0_ + kq * 32), db1 = kmajor_desc(b1_ + kq * 32);
                             const uint32_t accum = !(seg_start && kq == 0);
                             if (PRECISE) {
-                                mma_bf16(d, da0, db0, idesc, accum);                      // D1 += big * big
-                                mma_bf16(d + BN, da1, db0, idesc, accum);                 // D2 += small * big
-                                mma_bf16(d + BN, da0, db1, idesc, 1);                     //     + big * small
+                                mma_bf16(d, da0, db0, idesc, accum);                      // D1 += big * big   (this segment)
+                                mma_bf16(d2, da1, db0, idesc, !(f == 0 && kq == 0));      // D2 += small * big (whole tile)
+                                mma_bf16(d2, da0, db1, idesc, 1);                         //     + big * small
                             } else {
                                 mma_bf16(d, da0, db0, idesc, accum); mma_bf16(d, da1, db0, idesc, 1); mma_bf16(d, da0, db1, idesc, 1);
                             }
                         }
                         mma_commit(b_empty(s));
                         if (seg_end) { mma_commit(acc_full(abuf)); ++sg; }
+                        if (PRECISE && f == nflat - 1) mma_commit(d2_full(d2buf));
                     }
                     mma_commit(pl_empty(pbuf));
                 }
@@ -274,8 +285,8 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
         const int cstart = PRECISE ? (ew >> 2) * COLS : 0;
         const int nflat = p.nkb * taps;
         const int nseg = PRECISE ? (nflat + p.promo_taps - 1) / p.promo_taps : 1;
-        int sg = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int sg = 0, ti = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
             int x0, y0, b0, n0;
             tile_coords(tile, x0, y0, b0, n0);
             const int ex = x0 + (er & 7), ey = y0 + (er >> 3);
@@ -301,38 +312,57 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
                 }
             };
             if (PRECISE) {
-                // every segment (the last one included) is promoted into fp32 registers and its TMEM buffer handed back at
-                // once; the epilogue then runs from registers while the MMA warp is already filling the next tile's segments
+                // every D1 segment (the last one included) is promoted into fp32 registers and its TMEM buffer handed back
+                // at once; the whole-tile cross-term accumulator D2 is added once at the end; the epilogue then runs from
+                // registers while the MMA warp is already filling the next tile's segments
                 float racc[COLS];
 #pragma unroll
                 for (int j = 0; j < COLS; ++j) racc[j] = 0.f;
+                constexpr int G = COLS == 32 ? 2 : 1;          // 16-column groups per round: G TMEM loads in flight, one wait
+                const uint32_t lane_addr = tmem_d + ((uint32_t)(q4 * 32) << 16);
                 for (int seg = 0; seg < nseg; ++seg, ++sg) {
-                    const int abuf = sg % C::NACC;
-                    mbar_wait_t(acc_full(abuf), (sg / C::NACC) & 1, tr, w0);
+                    const int abuf = sg % C::ND1;
+                    mbar_wait_t(acc_full(abuf), (sg / C::ND1) & 1, tr, w0);
                     tc_fence_after();
-                    // G 16-column groups per round: 2G TMEM loads in flight, one wait
-                    constexpr int G = COLS == 32 ? 2 : 1;      // (64 columns per thread: the accumulators alone take 64 registers)
 #pragma unroll
                     for (int c = 0; c < COLS / 16; c += G) {
-                        uint32_t v[G][16], v2[G][16];
+                        uint32_t v[G][16];
 #pragma unroll
-                        for (int g = 0; g < G; ++g) {
-                            const uint32_t col = (uint32_t)(abuf * C::ACC_COLS + cstart + (c + g) * 16);
-                            tmem_ld16_async(tmem_d + ((uint32_t)(q4 * 32) << 16) + col, v[g]);
-                            tmem_ld16_async(tmem_d + ((uint32_t)(q4 * 32) << 16) + col + BN, v2[g]);
-                        }
+                        for (int g = 0; g < G; ++g)
+                            tmem_ld16_async(lane_addr + (uint32_t)(C::D1_COL0 + abuf * BN + cstart + (c + g) * 16), v[g]);
                         tmem_ld_wait();
 #pragma unroll
                         for (int g = 0; g < G; ++g) {
-                            reg_fence(v[g]); reg_fence(v2[g]);
+                            reg_fence(v[g]);
 #pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                racc[(c + g) * 16 + j] += fmaf(__uint_as_float(v2[g][j]), 1.f / 2048.f, __uint_as_float(v[g][j]));
+                            for (int j = 0; j < 16; ++j) racc[(c + g) * 16 + j] += __uint_as_float(v[g][j]);
                         }
                     }
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acc_empty(abuf));
+                }
+                {
+                    const int d2buf = ti % (C::ND2 ? C::ND2 : 1);
+                    mbar_wait_t(d2_full(d2buf), (ti / (C::ND2 ? C::ND2 : 1)) & 1, tr, w0);
+                    tc_fence_after();
+#pragma unroll
+                    for (int c = 0; c < COLS / 16; c += G) {
+                        uint32_t v[G][16];
+#pragma unroll
+                        for (int g = 0; g < G; ++g)
+                            tmem_ld16_async(lane_addr + (uint32_t)(d2buf * BN + cstart + (c + g) * 16), v[g]);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int g = 0; g < G; ++g) {
+                            reg_fence(v[g]);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) racc[(c + g) * 16 + j] = fmaf(__uint_as_float(v[g][j]), 1.f / 2048.f, racc[(c + g) * 16 + j]);
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(d2_empty(d2buf));
                 }
 #pragma unroll
                 for (int j = 0; j < COLS; j += 4) {
@@ -341,13 +371,13 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
                 }
             } else {
                 // one segment per tile: read, finish, store, hand the buffer back
-                const int abuf = sg % C::NACC;
-                mbar_wait_t(acc_full(abuf), (sg / C::NACC) & 1, tr, w0);
+                const int abuf = sg % C::ND1;
+                mbar_wait_t(acc_full(abuf), (sg / C::ND1) & 1, tr, w0);
                 tc_fence_after();
 #pragma unroll 1
                 for (int c = 0; c < COLS / 16; ++c) {
                     uint32_t v[16];
-                    tmem_ld16(tmem_d + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(abuf * C::ACC_COLS + cstart + c * 16), v);
+                    tmem_ld16(tmem_d + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(C::D1_COL0 + abuf * BN + cstart + c * 16), v);
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
                         float o[4] = {__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])};
