@@ -66,6 +66,11 @@ def g_pl():
     return Golden('pl.npz')
 
 
+@pytest.fixture(scope='session')
+def g_sg3d():
+    return Golden('sg3d.npz')
+
+
 def up_cases(g):
     """[(name, shape, filter taps or None, kwargs, wrapper)] as recorded by make_golden.py."""
     return [ast.literal_eval(str(s)) for s in g['up.cases']]

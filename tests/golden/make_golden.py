@@ -10,6 +10,8 @@ that the oracle and the GPU path can replay them.  Files (all small, committed):
     ops.npz      upfirdn2d / bias_act reference ops (thirdparty/stylegan3_ops, impl='ref') incl. gradients
     modules.npz  single StyleGAN2 modules (implementations/StyleGAN2/model.py) forward + gradients
     model.npz    small G/D: images, logits, losses, all parameter gradients, R1, 3-step trajectory
+    sg3d.npz     StyleGAN3-style discriminator (implementations/StyleGAN3/model.py:382-510): logits, D-loss and R1
+                 parameter gradients, conv2d_resample cases
     pl.npz       path-length penalty (implementations/StyleGAN2/utils.py:18-33): value, per-sample gradient norms,
                  all second-order parameter gradients, 4-step trajectory with a PL step and an R1 step
 """
@@ -374,13 +376,61 @@ def gen_pl():
     print('pl.npz', len(out))
 
 
+def gen_sg3d():
+    """StyleGAN3-style discriminator and conv2d_resample through the reference's own code (CPU, fp32)."""
+    from implementations.StyleGAN3 import model as sg3
+    from thirdparty.stylegan3_ops.ops import conv2d_resample as ref_cr
+    out = {}
+    torch.manual_seed(99)
+    # conv2d_resample cases: (name, ci, co, k, down, padding, use filter)
+    cases = [('same3', 6, 8, 3, 1, 1, False), ('down3', 8, 8, 3, 2, 1, True), ('down1', 6, 12, 1, 2, 0, True),
+             ('valid3', 4, 4, 3, 1, 0, False), ('same1', 3, 8, 1, 1, 0, False), ('asym3', 4, 6, 3, 1, [2, 0, 1, 1], False)]
+    out['cr.cases'] = np.array([repr(c) for c in cases])
+    f = ref_up.setup_filter([1, 3, 3, 1])
+    out['cr.f'] = A(f)
+    for name, ci, co, k, down, pad, use_f in cases:
+        x = torch.randn(2, ci, 18, 14, requires_grad=True)
+        w = torch.randn(co, ci, k, k, requires_grad=True)
+        y = ref_cr.conv2d_resample(x, w, f if use_f else None, 1, down, pad)
+        gy = torch.randn_like(y)
+        gx, gw = torch.autograd.grad(y, (x, w), gy)
+        for key, t in (('x', x), ('w', w), ('y', y), ('gy', gy), ('gx', gx), ('gw', gw)):
+            out[f'cr.{name}.{key}'] = A(t)
+    # the discriminator: 32 px, channels 8 -> 32, batch 8 (two minibatch-stddev groups of 4)
+    cfg = dict(image_size=32, in_channels=3, channels=8, max_channels=32, mbsd_group_size=4, mbsd_channels=1)
+    out['cfg'] = np.array(repr(cfg))
+    D = sg3.Discriminator(**cfg)
+    for k, v in D.state_dict().items():
+        out['D0.' + k] = A(v)
+    real = torch.rand(8, 3, 32, 32) * 2 - 1
+    fake = torch.rand(8, 3, 32, 32) * 2 - 1
+    out['real'] = A(real); out['fake'] = A(fake)
+    loss = NonSaturatingLoss()
+    lr, lf = D(real), D(fake)
+    out['logits_real'] = A(lr); out['logits_fake'] = A(lf)
+    d_loss = loss.d_loss(lr, lf)
+    out['d_loss'] = A(d_loss)
+    dg = torch.autograd.grad(d_loss, list(D.parameters()), allow_unused=True)
+    for (n_, p), g_ in zip(D.named_parameters(), dg):
+        out['dgrad.' + n_] = A(g_) if g_ is not None else np.zeros(p.shape, np.float32)
+    r1 = r1_regularizer()(real, D, None)
+    out['r1'] = A(r1)
+    r1g = torch.autograd.grad(r1, list(D.parameters()), allow_unused=True)
+    for (n_, p), g_ in zip(D.named_parameters(), r1g):
+        out['r1grad.' + n_] = A(g_) if g_ is not None else np.zeros(p.shape, np.float32)
+        out['r1none.' + n_] = np.array(g_ is None)
+    np.savez_compressed(os.path.join(HERE, 'sg3d.npz'), **out)
+    print('sg3d.npz', len(out))
+
+
 if __name__ == '__main__':
-    if len(sys.argv) > 1 and sys.argv[1] == 'pl':       # only the file added last (the others are unchanged)
-        gen_pl()
+    if len(sys.argv) > 1 and sys.argv[1] in ('pl', 'sg3d'):       # only one of the files added later (the others are unchanged)
+        dict(pl=gen_pl, sg3d=gen_sg3d)[sys.argv[1]]()
         sys.exit(0)
     gen_ops()
     gen_modules()
     gen_model()
     gen_pl()
-    for f in ('ops.npz', 'modules.npz', 'model.npz', 'pl.npz'):
+    gen_sg3d()
+    for f in ('ops.npz', 'modules.npz', 'model.npz', 'pl.npz', 'sg3d.npz'):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, 'KiB')

@@ -187,3 +187,41 @@ def test_training_trajectory_with_path_length(g_pl):
         assert rel_err(v.detach().numpy(), g_pl['G4.' + k]) < 1e-3 or np.abs(g_pl['G4.' + k]).max() < 1e-6, k
     for k, v in sd_e.items():
         assert rel_err(v.detach().numpy(), g_pl['E4.' + k]) < 1e-3 or np.abs(g_pl['E4.' + k]).max() < 1e-6, k
+
+
+def test_sg3_discriminator_and_conv2d_resample(g_sg3d):
+    """oracle/sg3d_torch.py against the reference's StyleGAN3-style discriminator (logits, D-loss and R1 gradients) and its
+    conv2d_resample (outputs and gradients of the down-sampling / padding cases)."""
+    from oracle import sg3d_torch as S
+    g = g_sg3d
+    f = torch.from_numpy(g['cr.f'])
+    for case in g['cr.cases']:
+        name, ci, co, k, down, pad, use_f = ast.literal_eval(str(case))
+        x = torch.from_numpy(g[f'cr.{name}.x']).requires_grad_(True)
+        w = torch.from_numpy(g[f'cr.{name}.w']).requires_grad_(True)
+        y = S.conv2d_resample(x, w, f if use_f else None, down, pad)
+        assert rel_err(y.detach().numpy(), g[f'cr.{name}.y']) < 1e-5, name
+        gx, gw = torch.autograd.grad(y, (x, w), torch.from_numpy(g[f'cr.{name}.gy']))
+        assert rel_err(gx.numpy(), g[f'cr.{name}.gx']) < 1e-5 and rel_err(gw.numpy(), g[f'cr.{name}.gw']) < 1e-5, name
+    sd = {k: torch.from_numpy(v.copy()).requires_grad_(not k.endswith('down_filter')) for k, v in g.sub('D0.').items()}
+    real, fake = torch.from_numpy(g['real']), torch.from_numpy(g['fake'])
+    lr, lf = S.discriminator(sd, real), S.discriminator(sd, fake)
+    assert rel_err(lr.detach().numpy(), g['logits_real']) < 1e-5 and rel_err(lf.detach().numpy(), g['logits_fake']) < 1e-5
+    names = [k for k, v in sd.items() if v.requires_grad]
+    d_loss = T.d_loss_ns(lr, lf)
+    assert abs(float(d_loss) - float(g['d_loss'])) < 1e-5 * abs(float(g['d_loss']))
+    dg = torch.autograd.grad(d_loss, [sd[k] for k in names], allow_unused=True)
+    for k, gr in zip(names, dg):
+        assert rel_err(gr.numpy(), g['dgrad.' + k]) < 2e-4 or np.abs(g['dgrad.' + k]).max() < 1e-12, k
+    x = real.clone().requires_grad_(True)
+    out = S.discriminator(sd, x)
+    gx, = torch.autograd.grad(out, x, torch.ones_like(out), create_graph=True)
+    r1 = gx.reshape(gx.shape[0], -1).norm(2, dim=1).pow(2).mean() / 2.
+    assert abs(float(r1) - float(g['r1'])) < 1e-5 * abs(float(g['r1']))
+    r1g = torch.autograd.grad(r1, [sd[k] for k in names], allow_unused=True)
+    for k, gr in zip(names, r1g):
+        ref = g['r1grad.' + k]
+        if gr is None:
+            assert bool(g['r1none.' + k]) or np.abs(ref).max() == 0, k
+        else:
+            assert rel_err(gr.numpy(), ref) < 2e-4 or np.abs(ref).max() < 1e-12, k
