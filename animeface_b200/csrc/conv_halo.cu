@@ -290,8 +290,9 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
             int x0, y0, b0, n0;
             tile_coords(tile, x0, y0, b0, n0);
             const int ex = x0 + (er & 7), ey = y0 + (er >> 3);
+            const bool inside = ex < p.w && ey < p.h;      // ragged images: tiles hang over the right / bottom edge
             const long long pix = ((long long)b0 * p.h + ey) * p.w + ex;
-            const float nz = p.noise ? __ldg(p.noise + pix) : 0.f;
+            const float nz = (p.noise && inside) ? __ldg(p.noise + pix) : 0.f;
             float* yrow = p.y + (long long)b0 * p.ys[0] + (long long)ey * p.ys[2] + (long long)ex * p.ys[3];
             const float* osc = p.out_scale ? p.out_scale + (long long)b0 * p.co + n0 + cstart : nullptr;
             const float* bsp = p.bias ? p.bias + n0 + cstart : nullptr;
@@ -305,6 +306,7 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
                     o[e] = val * p.gain;
                 }
                 const int cb = n0 + cstart + cbase;
+                if (!inside) return;
                 if (p.ys[1] == 1) st4(yrow + cb, make_float4(o[0], o[1], o[2], o[3]));
                 else {
 #pragma unroll
@@ -459,7 +461,10 @@ bool conv_halo_supported(int n, int h, int w, int ci, int co, int k) {
     if (k != 1 && k != 3) return false;
     if (ci % 32 != 0 || ci < 32) return false;
     if (!halo::pick_bn(co)) return false;
-    return (w % halo::TW) == 0 && (h % halo::TH) == 0 && w <= 4096 && h <= 4096;
+    if (w > 4096 || h > 4096) return false;
+    // images that tile exactly by 8 x 16, or large ragged ones (edge tiles are masked; e.g. the 257^2 blurred inputs of
+    // the StyleGAN3-style discriminator) -- small ragged images would waste most of every tile
+    return ((w % halo::TW) == 0 && (h % halo::TH) == 0) || (w >= 32 && h >= 32);
 }
 
 long long conv_packed_bytes_halo(int co, int ci, int k) {
@@ -499,7 +504,7 @@ int conv_fwd_halo(const ConvParams& p, int precise, cudaStream_t st) {
     for (int i = 0; i < 4; ++i) tp.ys[i] = p.ys[i];
     tp.wp = (const unsigned char*)p.wp;
     tp.n = p.n; tp.h = p.h; tp.w = p.w; tp.ci = p.ci; tp.co = p.co; tp.k = p.k;
-    tp.tiles_x = p.w / halo::TW; tp.tiles_y = p.h / halo::TH;
+    tp.tiles_x = (p.w + halo::TW - 1) / halo::TW; tp.tiles_y = (p.h + halo::TH - 1) / halo::TH;
     tp.m_tiles = tp.tiles_x * tp.tiles_y * p.n;
     const int bn = halo::pick_bn(p.co);
     tp.n_tiles = p.co / bn;

@@ -208,6 +208,14 @@ static inline bool pixel_box(int total, int h, int w, int& bw, int& bh, int& bb)
     bb = total / (bw * bh);
     return bw * bh * bb == total && bb <= 256;
 }
+// The same for kernels that accept ragged images: any image at least `total` pixels wide is cut into row pieces of
+// `total` pixels; the last piece of a row hangs over the edge (TMA fills the overhang with zeros on load).
+static inline bool pixel_box_ragged(int total, int h, int w, int& bw, int& bh, int& bb) {
+    if (pixel_box(total, h, w, bw, bh, bb)) return true;
+    if (w < total || w > 8192 || h < 1 || h > 8192) return false;
+    bw = total; bh = 1; bb = 1;
+    return true;
+}
 
 }  // namespace tc
 }  // namespace sg2

@@ -304,12 +304,12 @@ bool wgrad_tc_supported(int n, int h, int w, int ci, int co, int k) {
     if (k != 1 && k != 3) return false;
     if (ci % 32 != 0 || co % 32 != 0) return false;
     int a, b, c;
-    return tc::pixel_box(wg::CHUNK, h, w, a, b, c);
+    return tc::pixel_box_ragged(wg::CHUNK, h, w, a, b, c);
 }
 
 int conv_wgrad_tc(WgradParams wp, int accumulate, cudaStream_t st) {
     wg::Params p;
-    if (!tc::pixel_box(wg::CHUNK, wp.h, wp.w, p.cw, p.ch, p.cb)) return fail(SG2_ENOTSUP, "conv_wgrad_tc: unsupported shape");
+    if (!tc::pixel_box_ragged(wg::CHUNK, wp.h, wp.w, p.cw, p.ch, p.cb)) return fail(SG2_ENOTSUP, "conv_wgrad_tc: unsupported shape");
     if (4 * 64 + 4 * (p.cw + wp.k - 1) * p.ch * p.cb > 32 * wg::XWARPS || (p.cw + wp.k - 1) * p.ch * p.cb > wg::XROWS_MAX)
         return fail(SG2_ENOTSUP, "conv_wgrad_tc: chunk %dx%dx%d does not fit the transform", p.cw, p.ch, p.cb);
     const int kk2 = wp.k * wp.k;
@@ -325,7 +325,7 @@ int conv_wgrad_tc(WgradParams wp, int accumulate, cudaStream_t st) {
     p.in_scale = wp.in_scale; p.out_scale = wp.out_scale; p.dw = wp.dw; p.coef = wp.coef; p.trace = g_trace;
     p.n = wp.n; p.h = wp.h; p.w = wp.w; p.ci = wp.ci; p.co = wp.co; p.k = wp.k;
     p.xb = (((p.cw + wp.k - 1) * p.ch * p.cb * 128) + 1023) / 1024 * 1024;
-    p.chunks_x = wp.w / p.cw; p.chunks_y = wp.h / p.ch;
+    p.chunks_x = (wp.w + p.cw - 1) / p.cw; p.chunks_y = (wp.h + p.ch - 1) / p.ch;      // ragged: the last chunk of a row overhangs
     p.total_chunks = p.chunks_x * p.chunks_y * ((wp.n + p.cb - 1) / p.cb);
     p.co_tiles = (wp.co + wg::MT - 1) / wg::MT;
     p.ci_tiles = (wp.ci + wg::NT_CI - 1) / wg::NT_CI;

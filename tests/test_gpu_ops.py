@@ -342,6 +342,36 @@ def test_flat_adam_matches_torch_adam_and_skips_none_grads():
         assert rel_err(N(pb), N(pa)) < 1e-5
 
 
+@pytest.mark.parametrize('n,ci,co,k,h,w', [(2, 64, 64, 3, 33, 41), (1, 32, 128, 3, 65, 37), (3, 64, 32, 1, 40, 52), (2, 128, 64, 3, 129, 129)])
+def test_tcgen05_ragged_images_vs_fp64(n, ci, co, k, h, w):
+    """Images that do not tile by 8 x 16 (halo kernels: masked edge tiles) / by 32-pixel row pieces (wgrad: zero-filled
+    overhang) -- the blurred 257^2 / 129^2 inputs of the StyleGAN3-style discriminator's down-sampling convolutions."""
+    from animeface_b200.ops import conv2d as C
+    import torch.nn.functional as F
+    g = torch.Generator(device=DEV).manual_seed(h * w + ci)
+    x = torch.randn(n, ci, h, w, device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    wt = torch.randn(co, ci, k, k, device=DEV, generator=g)
+    s = torch.randn(n, ci, device=DEV, generator=g)
+    d = torch.rand(n, co, device=DEV, generator=g) + 0.5
+    b = torch.randn(co, device=DEV, generator=g)
+    nz = torch.randn(n, 1, h, w, device=DEV, generator=g)
+    gy = torch.randn(n, co, h, w, device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    coef = 0.05
+    ref = F.leaky_relu(F.conv2d((x * s[:, :, None, None]).double(), (wt * coef).double(), padding=k // 2) * d[:, :, None, None].double()
+                       + b[None, :, None, None].double() + nz.double(), 0.2)
+    for impl, tol in ((5, 3e-6), (4, 5e-5)):
+        y = C._conv_raw(x, wt, coef, False, in_scale=s, out_scale=d, bias=b, noise=nz, slope=0.2, impl=impl)
+        assert rel_err(N(y), N(ref)) < tol, impl
+    gx = C._conv_raw(gy, wt, coef, True, impl=4)
+    assert rel_err(N(gx), N(F.conv_transpose2d(gy.double(), (wt * coef).double(), padding=k // 2))) < 5e-5
+    if w >= 32:
+        wd = torch.zeros(co, ci, k, k, device=DEV, dtype=torch.float64, requires_grad=True)
+        yr = F.conv2d((x * s[:, :, None, None]).double(), wd * coef, padding=k // 2) * d[:, :, None, None].double()
+        ref_w, = torch.autograd.grad(yr, wd, gy.double())
+        dw = C._wgrad_raw(x, gy, k, coef, in_scale=s, out_scale=d, impl=2)
+        assert rel_err(N(dw), N(ref_w)) < 5e-5
+
+
 # ------------------------------------------------------------------------- tcgen05 kernels, every variant
 @pytest.mark.parametrize('impl,tol', [(2, 5e-5), (3, 3e-6), (4, 5e-5), (5, 3e-6)])
 @pytest.mark.parametrize('n,ci,co,k,hw', [(2, 64, 64, 3, 16), (8, 32, 64, 3, 16), (3, 64, 128, 3, 32), (4, 128, 32, 1, 16), (1, 256, 256, 3, 16)])
