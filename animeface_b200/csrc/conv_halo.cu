@@ -32,7 +32,6 @@ constexpr int SLOT_BYTES = 24 * 1024;      // 1024-aligned slot pitch
 constexpr int MAX_ROWS = (TW + 2) * (TH + 2);            // 180 patch rows
 constexpr int PLANE = 8 * MAX_ROWS * 16;                 // 8 chunks x rows x 16 B = 23040 B
 constexpr int PLANE_PITCH = 23 * 1024;                   // 23552
-constexpr int BSTAGES = 3;
 
 template <int BN, bool PRECISE> struct Cfg {
     static constexpr int EPI_WARPS = PRECISE ? 8 : 4;
@@ -43,16 +42,17 @@ template <int BN, bool PRECISE> struct Cfg {
     static constexpr int BOXES = 2;                                // TMA boxes (32 ch) per block
     static constexpr int SLOTS = BN == 128 ? 1 : 2;                // staging slots (boxes in flight); 1 keeps BN=128 under 227 KB
     static constexpr int BTILE = 2 * BN * 128;                     // two planes of [BN rows x 128 B]
+    // weight stages: as deep as the 227 KB allow (the weight tiles stream from L2 once per pixel tile and tap)
+    static constexpr int BSTAGES = BN == 128 ? 3 : (BN == 64 ? 5 : 6);
     static constexpr int SMEM = 1024 + SLOTS * SLOT_BYTES + 2 * 2 * PLANE_PITCH + BSTAGES * BTILE + 256;
-    // TMEM accumulators (BN fp32 columns each).  D1 buffers take the big*big products of one segment (promoted into
-    // registers and handed back segment by segment; the promotion latency hides behind ND1 - 1 segments of MMA work).
-    // PRECISE only: D2 buffers take the cross terms small*big + big*small of a WHOLE tile -- they are 2^-11 of the result,
-    // so the accumulator truncation that forces D1's short chains is irrelevant for them, and they are read once per tile.
-    static constexpr int ND2 = PRECISE ? (BN == 128 ? 1 : 2) : 0;
-    static constexpr int ND1 = PRECISE ? (BN == 128 ? 3 : 4) : 4;
-    static constexpr int D1_COL0 = ND2 * BN;                       // D2 buffers first, then the D1 buffers
-    static constexpr uint32_t TMEM_COLS = (ND1 + ND2) * BN <= 32 ? 32 : ((ND1 + ND2) * BN <= 64 ? 64 : ((ND1 + ND2) * BN <= 128 ? 128 :
-                                          ((ND1 + ND2) * BN <= 256 ? 256 : 512)));
+    // One TMEM accumulator buffer = 2*BN fp32 columns: the first MMA of a k16 step multiplies the big / hi A plane by BOTH
+    // weight planes at once (B rows = [plane0 ; plane1], N = 2*BN), so columns [0,BN) collect big*big (hi*hi) and columns
+    // [BN,2BN) the cross term big*small (hi*lo); the second MMA adds small*big (lo*hi) into the upper half.  Two MMAs
+    // instead of three per k16 step: A is fetched from shared memory twice instead of three times (the MMA rate of this
+    // kernel is set by that operand fetch).  PRECISE: lower half = D1 (promoted segment by segment), upper half = D2.
+    static constexpr int ACC_COLS = 2 * BN;
+    static constexpr int NACC = 512 / ACC_COLS >= 4 ? 4 : 512 / ACC_COLS;       // buffers: promotion / epilogue latency hides behind NACC-1 segments
+    static constexpr uint32_t TMEM_COLS = NACC * ACC_COLS;
 };
 
 struct Params {
@@ -82,18 +82,17 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
     const uint32_t slot_base = base;
     const uint32_t plane_base = slot_base + C::SLOTS * SLOT_BYTES;            // [buf][plane]
     const uint32_t b_base = plane_base + 4 * PLANE_PITCH;
+    constexpr int BSTAGES = C::BSTAGES;
     const uint32_t bar_base = b_base + BSTAGES * C::BTILE;
     auto st_full = [&](int s) { return bar_base + 8u * s; };                  // 2
     auto st_empty = [&](int s) { return bar_base + 16u + 8u * s; };           // 2
     auto pl_full = [&](int b) { return bar_base + 32u + 8u * b; };            // 2
     auto pl_empty = [&](int b) { return bar_base + 48u + 8u * b; };           // 2
-    auto b_full = [&](int s) { return bar_base + 64u + 8u * s; };             // 3
-    auto b_empty = [&](int s) { return bar_base + 88u + 8u * s; };            // 3
-    auto acc_full = [&](int b) { return bar_base + 112u + 8u * b; };          // ND1 <= 4
-    auto acc_empty = [&](int b) { return bar_base + 144u + 8u * b; };         // ND1 <= 4
-    auto d2_full = [&](int b) { return bar_base + 176u + 8u * b; };           // ND2 <= 2
-    auto d2_empty = [&](int b) { return bar_base + 192u + 8u * b; };          // ND2 <= 2
-    const uint32_t tmem_slot = bar_base + 208u;
+    auto b_full = [&](int s) { return bar_base + 64u + 8u * s; };             // BSTAGES <= 6
+    auto b_empty = [&](int s) { return bar_base + 112u + 8u * s; };           // BSTAGES <= 6
+    auto acc_full = [&](int b) { return bar_base + 160u + 8u * b; };          // NACC <= 4
+    auto acc_empty = [&](int b) { return bar_base + 192u + 8u * b; };         // NACC <= 4
+    const uint32_t tmem_slot = bar_base + 224u;
     auto plane = [&](int buf, int pl) { return plane_base + (uint32_t)((buf * 2 + pl) * PLANE_PITCH); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -118,8 +117,7 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
             mbar_init(st_full(s), 1); mbar_init(st_empty(s), 8);
             mbar_init(pl_full(s), 8); mbar_init(pl_empty(s), 1);
         }
-        for (int s = 0; s < C::ND1; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), C::EPI_WARPS); }
-        for (int s = 0; s < C::ND2; ++s) { mbar_init(d2_full(s), 1); mbar_init(d2_empty(s), C::EPI_WARPS); }
+        for (int s = 0; s < C::NACC; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), C::EPI_WARPS); }
         for (int s = 0; s < BSTAGES; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
         fence_barrier_init();
     }
@@ -167,12 +165,10 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (elect_one()) {
-            constexpr uint32_t idesc = PRECISE ? idesc_f16(BM, BN) : idesc_bf16(BM, BN);
-            int bt = 0, kbg = 0, sg = 0, ti = 0;          // global weight-tile / channel-block / accumulator-segment / tile counters
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-                const int d2buf = PRECISE ? ti % (C::ND2 ? C::ND2 : 1) : 0;
-                if (PRECISE) mbar_wait_t(d2_empty(d2buf), ((ti / (C::ND2 ? C::ND2 : 1)) & 1) ^ 1, tr, w2);
-                const uint32_t d2 = tmem_d + (uint32_t)(d2buf * BN);
+            constexpr uint32_t idesc = PRECISE ? idesc_f16(BM, BN) : idesc_bf16(BM, BN);              // N = BN
+            constexpr uint32_t idesc2 = PRECISE ? idesc_f16(BM, 2 * BN) : idesc_bf16(BM, 2 * BN);     // N = 2 BN (both weight planes)
+            int bt = 0, kbg = 0, sg = 0;                  // global weight-tile / channel-block / accumulator-segment counters
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 int f = 0, fseg = 0;                      // flat (kb, tap) index inside the tile / inside the accumulator segment
                 const int nflat = p.nkb * taps;
                 for (int kb = 0; kb < p.nkb; ++kb, ++kbg) {
@@ -183,31 +179,24 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
                         const bool seg_start = PRECISE ? (fseg == 0) : (f == 0);
                         const bool seg_end = PRECISE ? (fseg == p.promo_taps - 1 || f == nflat - 1) : (f == nflat - 1);
                         fseg = seg_end ? 0 : fseg + 1;
-                        const int abuf = sg % C::ND1;
-                        if (seg_start) mbar_wait_t(acc_empty(abuf), ((sg / C::ND1) & 1) ^ 1, tr, w2);
+                        const int abuf = sg % C::NACC;
+                        if (seg_start) mbar_wait_t(acc_empty(abuf), ((sg / C::NACC) & 1) ^ 1, tr, w2);
                         const int s = bt % BSTAGES;
                         mbar_wait_t(b_full(s), (bt / BSTAGES) & 1, tr, w1);
                         tc_fence_after();
-                        const uint32_t d = tmem_d + (uint32_t)(C::D1_COL0 + abuf * BN);
+                        const uint32_t d = tmem_d + (uint32_t)(abuf * C::ACC_COLS);
                         const uint32_t arow = (uint32_t)(dy * PW + dx) * 16u;
                         const uint32_t a0 = plane(pbuf, 0) + arow, a1 = plane(pbuf, 1) + arow;
-                        const uint32_t b0_ = b_base + s * C::BTILE, b1_ = b0_ + BN * 128;
+                        const uint32_t b0_ = b_base + s * C::BTILE;       // plane 0 rows, then plane 1 rows: 2*BN contiguous B rows
 #pragma unroll
                         for (int kq = 0; kq < 4; ++kq) {
                             const uint64_t da0 = interleave_desc(a0 + 2 * kq * LBO, LBO, SBO), da1 = interleave_desc(a1 + 2 * kq * LBO, LBO, SBO);
-                            const uint64_t db0 = kmajor_desc(b0_ + kq * 32), db1 = kmajor_desc(b1_ + kq * 32);
-                            const uint32_t accum = !(seg_start && kq == 0);
-                            if (PRECISE) {
-                                mma_bf16(d, da0, db0, idesc, accum);                      // D1 += big * big   (this segment)
-                                mma_bf16(d2, da1, db0, idesc, !(f == 0 && kq == 0));      // D2 += small * big (whole tile)
-                                mma_bf16(d2, da0, db1, idesc, 1);                         //     + big * small
-                            } else {
-                                mma_bf16(d, da0, db0, idesc, accum); mma_bf16(d, da1, db0, idesc, 1); mma_bf16(d, da0, db1, idesc, 1);
-                            }
+                            const uint64_t db = kmajor_desc(b0_ + kq * 32);
+                            mma_bf16(d, da0, db, idesc2, !(seg_start && kq == 0));        // [D1 | D2] += A0 * [B0 ; B1]
+                            mma_bf16(d + BN, da1, db, idesc, 1);                          //       D2  += A1 * B0
                         }
                         mma_commit(b_empty(s));
                         if (seg_end) { mma_commit(acc_full(abuf)); ++sg; }
-                        if (PRECISE && f == nflat - 1) mma_commit(d2_full(d2buf));
                     }
                     mma_commit(pl_empty(pbuf));
                 }
@@ -285,8 +274,8 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
         const int cstart = PRECISE ? (ew >> 2) * COLS : 0;
         const int nflat = p.nkb * taps;
         const int nseg = PRECISE ? (nflat + p.promo_taps - 1) / p.promo_taps : 1;
-        int sg = 0, ti = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+        int sg = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             int x0, y0, b0, n0;
             tile_coords(tile, x0, y0, b0, n0);
             const int ex = x0 + (er & 7), ey = y0 + (er >> 3);
@@ -313,58 +302,40 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
                     for (int e = 0; e < 4; ++e) yrow[(long long)(cb + e) * p.ys[1]] = o[e];
                 }
             };
+            const uint32_t lane_addr = tmem_d + ((uint32_t)(q4 * 32) << 16);
             if (PRECISE) {
-                // every D1 segment (the last one included) is promoted into fp32 registers and its TMEM buffer handed back
-                // at once; the whole-tile cross-term accumulator D2 is added once at the end; the epilogue then runs from
-                // registers while the MMA warp is already filling the next tile's segments
+                // every segment (the last one included) is promoted into fp32 registers -- acc += D1 + 2^-11 D2 -- and its
+                // TMEM buffer handed back at once; the epilogue then runs from registers while the MMA warp is already
+                // filling the next tile's segments
                 float racc[COLS];
 #pragma unroll
                 for (int j = 0; j < COLS; ++j) racc[j] = 0.f;
-                constexpr int G = COLS == 32 ? 2 : 1;          // 16-column groups per round: G TMEM loads in flight, one wait
-                const uint32_t lane_addr = tmem_d + ((uint32_t)(q4 * 32) << 16);
+                constexpr int G = COLS == 32 ? 2 : 1;          // 16-column groups per round: 2G TMEM loads in flight, one wait
                 for (int seg = 0; seg < nseg; ++seg, ++sg) {
-                    const int abuf = sg % C::ND1;
-                    mbar_wait_t(acc_full(abuf), (sg / C::ND1) & 1, tr, w0);
+                    const int abuf = sg % C::NACC;
+                    mbar_wait_t(acc_full(abuf), (sg / C::NACC) & 1, tr, w0);
                     tc_fence_after();
 #pragma unroll
                     for (int c = 0; c < COLS / 16; c += G) {
-                        uint32_t v[G][16];
+                        uint32_t v[G][16], v2[G][16];
 #pragma unroll
-                        for (int g = 0; g < G; ++g)
-                            tmem_ld16_async(lane_addr + (uint32_t)(C::D1_COL0 + abuf * BN + cstart + (c + g) * 16), v[g]);
+                        for (int g = 0; g < G; ++g) {
+                            const uint32_t col = (uint32_t)(abuf * C::ACC_COLS + cstart + (c + g) * 16);
+                            tmem_ld16_async(lane_addr + col, v[g]);
+                            tmem_ld16_async(lane_addr + col + BN, v2[g]);
+                        }
                         tmem_ld_wait();
 #pragma unroll
                         for (int g = 0; g < G; ++g) {
-                            reg_fence(v[g]);
+                            reg_fence(v[g]); reg_fence(v2[g]);
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) racc[(c + g) * 16 + j] += __uint_as_float(v[g][j]);
+                            for (int j = 0; j < 16; ++j)
+                                racc[(c + g) * 16 + j] += fmaf(__uint_as_float(v2[g][j]), 1.f / 2048.f, __uint_as_float(v[g][j]));
                         }
                     }
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acc_empty(abuf));
-                }
-                {
-                    const int d2buf = ti % (C::ND2 ? C::ND2 : 1);
-                    mbar_wait_t(d2_full(d2buf), (ti / (C::ND2 ? C::ND2 : 1)) & 1, tr, w0);
-                    tc_fence_after();
-#pragma unroll
-                    for (int c = 0; c < COLS / 16; c += G) {
-                        uint32_t v[G][16];
-#pragma unroll
-                        for (int g = 0; g < G; ++g)
-                            tmem_ld16_async(lane_addr + (uint32_t)(d2buf * BN + cstart + (c + g) * 16), v[g]);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int g = 0; g < G; ++g) {
-                            reg_fence(v[g]);
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) racc[(c + g) * 16 + j] = fmaf(__uint_as_float(v[g][j]), 1.f / 2048.f, racc[(c + g) * 16 + j]);
-                        }
-                    }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(d2_empty(d2buf));
                 }
 #pragma unroll
                 for (int j = 0; j < COLS; j += 4) {
@@ -372,17 +343,22 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
                     finish4(o, j);
                 }
             } else {
-                // one segment per tile: read, finish, store, hand the buffer back
-                const int abuf = sg % C::ND1;
-                mbar_wait_t(acc_full(abuf), (sg / C::ND1) & 1, tr, w0);
+                // one segment per tile: read both halves (hi*hi | hi*lo + lo*hi), add, finish, store, hand the buffer back
+                const int abuf = sg % C::NACC;
+                mbar_wait_t(acc_full(abuf), (sg / C::NACC) & 1, tr, w0);
                 tc_fence_after();
 #pragma unroll 1
                 for (int c = 0; c < COLS / 16; ++c) {
-                    uint32_t v[16];
-                    tmem_ld16(tmem_d + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(C::D1_COL0 + abuf * BN + cstart + c * 16), v);
+                    uint32_t v[16], v2[16];
+                    const uint32_t col = (uint32_t)(abuf * C::ACC_COLS + cstart + c * 16);
+                    tmem_ld16_async(lane_addr + col, v);
+                    tmem_ld16_async(lane_addr + col + BN, v2);
+                    tmem_ld_wait();
+                    reg_fence(v); reg_fence(v2);
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
-                        float o[4] = {__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])};
+                        float o[4] = {__uint_as_float(v[j]) + __uint_as_float(v2[j]), __uint_as_float(v[j + 1]) + __uint_as_float(v2[j + 1]),
+                                      __uint_as_float(v[j + 2]) + __uint_as_float(v2[j + 2]), __uint_as_float(v[j + 3]) + __uint_as_float(v2[j + 3])};
                         finish4(o, c * 16 + j);
                     }
                 }

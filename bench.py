@@ -123,6 +123,44 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------------
+def upfirdn2d_rates(dev, peaks):
+    """Achieved HBM GB/s of the upfirdn2d-family kernels on SURVEY 8(d)'s inputs (algorithmic bytes = one read of x + one
+    write of y), CUDA events, L2 flushed between iterations, median of 7."""
+    import torch
+    from animeface_b200.ops import upfirdn2d as U
+    from animeface_b200.ops.resample import avgpool2, upsample2x_blur
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def rate(fn, nbytes):
+        for _ in range(2):
+            fn()
+        ts = []
+        for _ in range(7):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ms = sorted(ts)[len(ts) // 2]
+        gbs = nbytes / ms / 1e6
+        return dict(ms=round(ms, 4), GBps=round(gbs, 1), frac=round(gbs / peaks['hbm'], 3))
+
+    cl = lambda *shape: torch.randn(*shape, device=dev).contiguous(memory_format=torch.channels_last)
+    out = {}
+    with torch.no_grad():
+        x = cl(32, 64, 128, 128)
+        out['U1 up2 bilinear+blur [32,64,128,128]->256^2 (fused, SG2 generator)'] = rate(lambda: upsample2x_blur(x), x.numel() * 4 * 5)
+        g = cl(32, 64, 256, 256)
+        out['U3 down2 [1,1] = AvgPool2 [32,64,256,256] (SG2 discriminator)'] = rate(lambda: avgpool2(g), g.numel() * 4 * 1.25)
+        f = U.setup_filter([1, 3, 3, 1], device=dev)
+        out['U4 filter 4x4 pad 2 -> 257^2, NHWC (SG3-style discriminator)'] = rate(lambda: U.upfirdn2d(g, f, padding=2), (g.numel() + 32 * 64 * 257 * 257) * 4)
+        out['U4 down2 4x4 pad 1 -> 128^2, NHWC'] = rate(lambda: U.upfirdn2d(g, f, down=2, padding=1), g.numel() * 4 * 1.25)
+        gc = g.contiguous()
+        out['U4 filter 4x4 pad 2 -> 257^2, NCHW'] = rate(lambda: U.upfirdn2d(gc, f, padding=2), (g.numel() + 32 * 64 * 257 * 257) * 4)
+    out['peak_GBps'] = peaks['hbm']
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -219,7 +257,11 @@ def run_b200(args):
                     share_of_step=round(conv_ms / max(ms, 1e-9), 3),
                     launches=len(conv_log),
                     by_kind={k: dict(tflops=round(v[0] / (v[1] / 1e3) / 1e12, 2), ms=round(v[1], 2), launches=v[2])
-                             for k, v in by_kind.items()})
+                             for k, v in by_kind.items()},
+                    mma_per_product=3,
+                    note='fp32 operands are split into two 16-bit planes (fp32-class results, DESIGN 3.1): every algorithmic '
+                         'product costs 3 tensor-core MMAs, so the tensor pipe does 3x `achieved`; ncu tensor-pipe-active '
+                         'and DRAM bytes per launch: profiles/r1c_ncu_full_conv_wgrad.txt')
 
     # ---- end-to-end: host batch in pinned memory -> H2D each step, losses read back each step
     host = [torch.empty(B, 3, 256, 256, pin_memory=True).uniform_(-1, 1) for _ in range(2)]
@@ -251,6 +293,8 @@ def run_b200(args):
     if rank != 0:
         finish()
         return
+    # second half of BASELINE.json's metric: upfirdn2d achieved HBM GB/s on the SURVEY 8(d) inputs (rank 0, N = 1 only)
+    upf = upfirdn2d_rates(dev, peaks) if world == 1 else None
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         ips, sec, cores = cpu_oracle_step_rate(4, 2, 1)
@@ -266,7 +310,8 @@ def run_b200(args):
                             l2='per-step working set (activations, several GB) >> 126 MB L2; no explicit flush',
                             r1_steps_in_timed_region=sum(1 for i in range(args.steps) if (args.warmup + i) % cfg.d_k == 0 and (args.warmup + i) != 0),
                             model_tflops=round(value * FLOP_PER_IMG_STEP / 1e12, 2)),
-                clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu_baseline)
+                clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu_baseline,
+                upfirdn2d=upf)
     print(json.dumps(line), flush=True)
     finish()
 
