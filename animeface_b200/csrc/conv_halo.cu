@@ -433,14 +433,18 @@ static int launch(const CUtensorMap& map, const Params& tp, dim3 grid, cudaStrea
 }  // namespace halo
 
 bool conv_halo_supported(int n, int h, int w, int ci, int co, int k) {
-    (void)n;
     if (k != 1 && k != 3) return false;
     if (ci % 32 != 0 || ci < 32) return false;
-    if (!halo::pick_bn(co)) return false;
+    const int bn = halo::pick_bn(co);
+    if (!bn) return false;
     if (w > 4096 || h > 4096) return false;
     // images that tile exactly by 8 x 16, or large ragged ones (edge tiles are masked; e.g. the 257^2 blurred inputs of
-    // the StyleGAN3-style discriminator) -- small ragged images would waste most of every tile
-    return ((w % halo::TW) == 0 && (h % halo::TH) == 0) || (w >= 32 && h >= 32);
+    // the StyleGAN3-style discriminator) ...
+    if (((w % halo::TW) == 0 && (h % halo::TH) == 0) || (w >= 32 && h >= 32)) return true;
+    // ... or small images (4^2, 8^2) whose tiles, however empty, all fit the machine at once: one 8 x 16 tile per image
+    // wastes most of its rows, but every CTA runs the full-rate pipeline in a single wave, which beats the per-tap kernels
+    const long long tiles = (long long)((w + halo::TW - 1) / halo::TW) * ((h + halo::TH - 1) / halo::TH) * n * (co / bn);
+    return w >= 4 && h >= 4 && tiles <= 2LL * num_sms();
 }
 
 long long conv_packed_bytes_halo(int co, int ci, int k) {

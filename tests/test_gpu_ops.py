@@ -342,7 +342,8 @@ def test_flat_adam_matches_torch_adam_and_skips_none_grads():
         assert rel_err(N(pb), N(pa)) < 1e-5
 
 
-@pytest.mark.parametrize('n,ci,co,k,h,w', [(2, 64, 64, 3, 33, 41), (1, 32, 128, 3, 65, 37), (3, 64, 32, 1, 40, 52), (2, 128, 64, 3, 129, 129)])
+@pytest.mark.parametrize('n,ci,co,k,h,w', [(2, 64, 64, 3, 33, 41), (1, 32, 128, 3, 65, 37), (3, 64, 32, 1, 40, 52), (2, 128, 64, 3, 129, 129),
+                                            (32, 512, 512, 3, 4, 4), (16, 256, 128, 3, 8, 8), (5, 64, 64, 1, 4, 8)])
 def test_tcgen05_ragged_images_vs_fp64(n, ci, co, k, h, w):
     """Images that do not tile by 8 x 16 (halo kernels: masked edge tiles) / by 32-pixel row pieces (wgrad: zero-filled
     overhang) -- the blurred 257^2 / 129^2 inputs of the StyleGAN3-style discriminator's down-sampling convolutions."""
