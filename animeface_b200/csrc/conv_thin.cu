@@ -107,6 +107,49 @@ __global__ void __launch_bounds__(256) thin_out_kernel(ConvParams p) {
     }
 }
 
+// Few input channels (ci <= 64, k = 1: the ToImage layers at 128^2 / 256^2): one thread per pixel.  A warp's 32 pixels are
+// contiguous in x, so its float4 loads sweep one contiguous span and its stores are coalesced per output plane -- no
+// shuffle tree, no lanes idling in the store.
+template <int COUT>
+__global__ void __launch_bounds__(256) thin_out_pix_kernel(ConvParams p) {
+    __shared__ __align__(16) float sw[COUT * 64];                  // [COUT][ci]
+    for (int i = threadIdx.x; i < COUT * p.ci; i += blockDim.x) {
+        const int o = i / p.ci, c = i % p.ci;
+        sw[i] = ((const float*)p.wp)[c * COUT + o];
+    }
+    __syncthreads();
+    const int hw = p.h * p.w, cq = p.ci >> 2;
+    const long long P = (long long)p.n * hw;
+    for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < P; pix += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(pix / hw), r = (int)(pix % hw), oy = r / p.w, ox = r % p.w;
+        const float* xp = p.x + pix * p.ci;
+        const float* sp = p.in_scale ? p.in_scale + (long long)b * p.ci : nullptr;
+        float acc[COUT];
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+        for (int q = 0; q < cq; ++q) {
+            float4 xv = ldg4(xp + 4 * q);
+            if (sp) xv = mul4(xv, ldg4(sp + 4 * q));
+#pragma unroll
+            for (int o = 0; o < COUT; ++o) {
+                const float4 w4 = *reinterpret_cast<const float4*>(&sw[o * p.ci + 4 * q]);
+                acc[o] = fmaf(xv.x, w4.x, fmaf(xv.y, w4.y, fmaf(xv.z, w4.z, fmaf(xv.w, w4.w, acc[o]))));
+            }
+        }
+        const float nz = p.noise ? __ldg(p.noise + pix) : 0.f;
+        float* yp = p.y + b * p.ys[0] + oy * p.ys[2] + ox * p.ys[3];
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) {
+            float v = acc[o];
+            if (p.out_scale) v *= __ldg(p.out_scale + (long long)b * COUT + o);
+            if (p.bias) v += __ldg(p.bias + o);
+            v += nz;
+            if (p.act == 3) v = v > 0.f ? v : v * p.alpha;
+            yp[(long long)o * p.ys[1]] = v * p.gain;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // R[c, t] = sum_pix wide[pix, c] * thin[pix, t]; grid = (splits, n): a block stays inside one sample so the per-sample
 // scales factor out of its partial sum.  dw[co][ci] gets R (thin side = ci) or R^T (thin side = co) through fp32 atomics.
@@ -188,6 +231,16 @@ int conv_fwd_thin(const ConvParams& p, cudaStream_t st) {
     }
     if (p.co <= 4 && (p.ci % 4) == 0 && p.k * p.k * p.ci * p.co <= thin::kMaxW && ((uintptr_t)p.x % 16) == 0) {
         const int cq = p.ci / 4;
+        if (p.k == 1 && p.ci <= 64 && P >= 65536) {
+            const int blocks = (int)std::min<long long>(ceil_div(P, 256), (long long)num_sms() * 16);
+            switch (p.co) {
+                case 1: thin::thin_out_pix_kernel<1><<<blocks, 256, 0, st>>>(p); break;
+                case 2: thin::thin_out_pix_kernel<2><<<blocks, 256, 0, st>>>(p); break;
+                case 3: thin::thin_out_pix_kernel<3><<<blocks, 256, 0, st>>>(p); break;
+                default: thin::thin_out_pix_kernel<4><<<blocks, 256, 0, st>>>(p); break;
+            }
+            return launched("conv_thin_out_pix");
+        }
         const int lanes = cq >= 32 ? 32 : (cq >= 16 ? 16 : (cq >= 8 ? 8 : 4));
         const int blocks = (int)std::min<long long>(ceil_div(P * lanes, 256), (long long)num_sms() * 16);
 #define SG2_THIN_OUT(CO, L) thin::thin_out_kernel<CO, L><<<blocks, 256, 0, st>>>(p)

@@ -256,7 +256,8 @@ def test_conv_family_vs_torch(ci, co, k, hw):
     assert rel_err(N(gx), N(rx)) < 1e-4 and rel_err(N(gw), N(rw)) < 1e-4
 
 
-@pytest.mark.parametrize('n,ci,co,hw', [(5, 3, 32, 24), (2, 3, 64, 8), (3, 32, 3, 20), (4, 512, 3, 4), (2, 128, 3, 16), (3, 4, 8, 6), (2, 64, 1, 8)])
+@pytest.mark.parametrize('n,ci,co,hw', [(5, 3, 32, 24), (2, 3, 64, 8), (3, 32, 3, 20), (4, 512, 3, 4), (2, 128, 3, 16), (3, 4, 8, 6), (2, 64, 1, 8),
+                                         (2, 32, 3, 200), (1, 64, 3, 260)])
 def test_thin_1x1_convs_vs_fp64(n, ci, co, hw):
     """RGB-side 1x1 layers (conv_thin.cu): fused forward incl. style / demod scales, bias, noise, lrelu and NCHW output,
     data gradient (the transposed layer is thin on the other side) and weight gradient with per-sample scales."""
