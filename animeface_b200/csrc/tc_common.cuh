@@ -28,44 +28,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "bra WAIT_LOOP;\n\t"
         "DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
-// ---- thread-block clusters: distributed shared memory + cluster-scope barriers -----------------------------------
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// address of the same shared-memory location in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void sts4_cluster(uint32_t caddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(caddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-// asynchronous 16-byte store into a peer CTA's shared memory; completion is counted (in bytes) on the peer's mbarrier
-// `cbar` like a TMA load -- no fence on the writer, the data is visible to whoever waits on that barrier phase
-__device__ __forceinline__ void st_async4(uint32_t caddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t cbar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
-                 ::"r"(caddr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(cbar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cbar) {        // cbar: a mapa() address
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cbar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {     // acquires remote CTAs' writes
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP_C:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_C;\n\t"
-        "bra WAIT_LOOP_C;\n\t"
-        "DONE_C:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void mma_commit_multicast(uint32_t bar, uint16_t cta_mask) {   // same barrier offset in every CTA of the mask
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"(cta_mask) : "memory");
-}
-
 // mbar_wait that adds the cycles spent waiting to `acc` when tracing is on (sg2_debug_trace)
 __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool trace, long long& acc) {
     if (trace) {

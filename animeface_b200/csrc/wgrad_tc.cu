@@ -15,7 +15,6 @@
 //           SWIZZLE_128B tiles (rows = pixels, 128 B = 64 channels); an x element is stored into the k dx-shifted tiles
 //   MMA   : 2 (k16) x 3 (hi*hi, lo*hi, hi*lo) tcgen05.mma 128 x N x 16 into one TMEM accumulator
 // Grid: (co tiles x ci tiles x k tap-rows) x pixel splits; partial sums are reduced with fp32 red.global.add.
-#include <stdlib.h>
 #include "tc_common.cuh"
 #include "conv.h"
 
@@ -57,18 +56,10 @@ struct Params {
     long long* trace;         // sg2_debug_trace buffer or null
 };
 
-// CL (k = 3 only): the three kernel-row CTAs (dy = 0, 1, 2) of one (co tile, ci tile, pixel split) form a thread-block
-// cluster.  They read the SAME gy chunk, so each converts a third of its rows and stores the bf16 planes into all three
-// CTAs' operand stages -- its own with plain stores, the peers' with st.async through distributed shared memory, whose
-// bytes are counted on the peer's "planes ready" barrier like a TMA load (no fence, no remote arrive).  The transform,
-// which bounds this kernel, does a third of the gy work per CTA.  "Planes free" becomes cluster-wide: every MMA warp's
-// commit is multicast to all three CTAs, because a peer writes into this CTA's stage.
-template <int KW, bool CL>
+template <int KW>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap gmap,
                                                                     const __grid_constant__ CUtensorMap xmap, const Params p) {
     using C = Cfg<KW>;
-    static_assert(!CL || KW == 3, "the cluster shares gy between the three kernel rows");
-    constexpr int NCTA = CL ? 3 : 1;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t f32_base = base;
@@ -88,13 +79,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_tc_kernel(const __grid
     long long* trow = p.trace + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16;
     const long long t_begin = tr ? clock64() : 0;
     long long w0 = 0, w1 = 0;
-    // tile: blockIdx.x = (dyi * ci_tiles + cit) * co_tiles + cot; clustered: the kernel row is the rank in the cluster,
-    // blockIdx.x = (cit * co_tiles + cot) * 3 + dyi
-    const int crank = CL ? (int)cluster_ctarank() : 0;
-    const int tix = CL ? blockIdx.x / 3 : blockIdx.x;
-    const int cot = tix % p.co_tiles;
-    const int cit = CL ? tix / p.co_tiles : (tix / p.co_tiles) % p.ci_tiles;
-    const int dyi = CL ? crank : tix / (p.co_tiles * p.ci_tiles);
+    // tile: blockIdx.x = (dyi * ci_tiles + cit) * co_tiles + cot
+    const int cot = blockIdx.x % p.co_tiles;
+    const int cit = (blockIdx.x / p.co_tiles) % p.ci_tiles;
+    const int dyi = blockIdx.x / (p.co_tiles * p.ci_tiles);
     const int co0 = cot * MT, ci0 = cit * NT_CI;
     const int pad = p.k >> 1;
     const int gy_boxes = min(4, (p.co - co0 + 31) / 32);      // gy boxes that hold real channels
@@ -106,14 +94,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_tc_kernel(const __grid
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < FS; ++s) { mbar_init(f_full(s), 1); mbar_init(f_empty(s), XWARPS); }
-        for (int s = 0; s < STAGES; ++s) { mbar_init(ab_full(s), XWARPS); mbar_init(ab_empty(s), NCTA); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(ab_full(s), XWARPS); mbar_init(ab_empty(s), 1); }
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
-    if (CL) cluster_sync();                       // every CTA's barriers are initialised before anyone arrives remotely
     tc_fence_after();
     uint32_t tmem_d;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_d) : "r"(tmem_slot));
@@ -148,7 +135,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_tc_kernel(const __grid
         if (nchunks > 0 && elect_one()) {
             constexpr uint32_t idesc = idesc_bf16_mn(MT, C::N);
             for (int i = 0, s = 0, ph = 0; i < nchunks; ++i) {
-                mbar_wait_t(ab_full(s), ph, tr, w0);      // local arrivals + (clustered) the peers' st.async bytes
+                mbar_wait_t(ab_full(s), ph, tr, w0);
                 tc_fence_after();
                 const uint32_t a_hi = bf_base + s * C::STAGE_BF, a_lo = a_hi + C::A_PLANE;
                 const uint32_t b_hi = a_lo + C::A_PLANE, b_lo = b_hi + C::B_PLANE;
@@ -161,8 +148,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_tc_kernel(const __grid
                     mma_bf16(tmem_d, dal, dbh, idesc, 1);
                     mma_bf16(tmem_d, dah, dbl, idesc, 1);
                 }
-                if (CL) mma_commit_multicast(ab_empty(s), (uint16_t)0x7);
-                else mma_commit(ab_empty(s));
+                mma_commit(ab_empty(s));
                 if (++s == STAGES) { s = 0; ph ^= 1; }
             }
             mma_commit(acc_full);
@@ -172,10 +158,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_tc_kernel(const __grid
         const int tt = threadIdx.x - 64;                 // 0 .. 32*XWARPS-1
         // One item = 16 channels of one box row; a chunk has gy_boxes*64 + 4*xrows <= 448 of them, so every thread owns at
         // most ONE item whose geometry is the same for all chunks: decode it (the integer divisions) once, up front.
-        // clustered: this CTA converts the gy rows r = 3k + rank (11 row slots per (box, half); slot 10 of rank 2 is empty)
-        const int gy_items = CL ? gy_boxes * 2 * 11 : gy_boxes * 64;   // (box, 16-channel half, pixel row)
+        const int gy_items = gy_boxes * 64;              // (box, 16-channel half, pixel row)
         const int x_items = 2 * 2 * xrows;               // (box, half, halo'd row)
-        bool active = tt < gy_items + x_items;
+        const bool active = tt < gy_items + x_items;
         const bool is_x = tt >= gy_items;
         // everything below is relative to the stage bases: src_off into the fp32 stage, dst[e][q] into the bf16 stage (hi
         // plane; the lo plane is lo_delta further), with the SWIZZLE_128B chunk permutation already applied
@@ -185,8 +170,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_tc_kernel(const __grid
             int j, r, half;
             uint32_t src_row;
             if (!is_x) {
-                if (CL) { const int u = tt / 11; j = u >> 1; half = u & 1; r = 3 * (tt % 11) + crank; active = r < CHUNK; }
-                else { j = tt >> 6; half = (tt >> 5) & 1; r = tt & 31; }
+                j = tt >> 6; half = (tt >> 5) & 1; r = tt & 31;
                 src_row = j * BOXB + r * 128;
                 const int sub = j & 1;                     // 32-channel sub-block inside the 64-wide MN block
                 for (int q = 0; q < 2; ++q) dst[0][q] = (j >> 1) * BOXB + r * 128 + (((4 * sub + 2 * half + q) ^ (r & 7)) << 4);
@@ -217,17 +201,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_tc_kernel(const __grid
             for (int q = 0; q < 4; ++q) src_off[q] = src_row + (((4 * half + q) ^ (r & 7)) << 4);
         }
         const int chunks_per_img = p.chunks_x * p.chunks_y;
-        // rows of a gy (box, half) converted by the peers: 32 minus this rank's share (11, 11, 10); 64 bytes per row item
-        const uint32_t peer_bytes = CL ? (uint32_t)(gy_boxes * 2 * (CHUNK - (crank == 2 ? 10 : 11)) * 64) : 0u;
         for (int i = 0, fs = 0, fph = 0, s = 0, sph = 0; i < nchunks; ++i) {
             mbar_wait_t(f_full(fs), fph, tr, w0);
-            if (CL) {
-                const long long t0 = tr ? clock64() : 0;
-                mbar_wait_cluster(ab_empty(s), sph ^ 1);            // stage s is free in all three CTAs
-                if (tr) w1 += clock64() - t0;
-            } else {
-                mbar_wait_t(ab_empty(s), sph ^ 1, tr, w1);
-            }
+            mbar_wait_t(ab_empty(s), sph ^ 1, tr, w1);
             if (active) {
                 const uint32_t src = f32_base + fs * stage_f32;
                 const uint32_t bf = bf_base + s * C::STAGE_BF;
@@ -251,46 +227,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_tc_kernel(const __grid
                 uint32_t hi[8], lo[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) split2(v[2 * q], v[2 * q + 1], hi[q], lo[q]);
-                if (CL && !is_x) {
-                    // gy: the same A-plane rows in all three CTAs of the cluster (own copy: plain stores)
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        if (c == crank) {
+                for (int e = 0; e < 3; ++e) {
+                    if (e < ndst) {
 #pragma unroll
-                            for (int q = 0; q < 2; ++q) {
-                                sts4(bf + dst[0][q], hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-                                sts4(bf + dst[0][q] + lo_delta, lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
-                            }
-                        } else {
-                            const uint32_t rbf = mapa(bf, (uint32_t)c), rbar = mapa(ab_full(s), (uint32_t)c);
-#pragma unroll
-                            for (int q = 0; q < 2; ++q) {
-                                st_async4(rbf + dst[0][q], hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3], rbar);
-                                st_async4(rbf + dst[0][q] + lo_delta, lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3], rbar);
-                            }
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 3; ++e) {
-                        if (e < ndst) {
-#pragma unroll
-                            for (int q = 0; q < 2; ++q) {
-                                sts4(bf + dst[e][q], hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-                                sts4(bf + dst[e][q] + lo_delta, lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
-                            }
+                        for (int q = 0; q < 2; ++q) {
+                            sts4(bf + dst[e][q], hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+                            sts4(bf + dst[e][q] + lo_delta, lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
                         }
                     }
                 }
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) {
-                // clustered: the first transform warp also announces the bytes the two peers will st.async into this stage
-                if (CL && tt == 0) mbar_expect_tx(ab_full(s), peer_bytes);
-                else mbar_arrive(ab_full(s));
-                mbar_arrive(f_empty(fs));
-            }
+            if (lane == 0) { mbar_arrive(ab_full(s)); mbar_arrive(f_empty(fs)); }
             if (++fs == FS) { fs = 0; fph ^= 1; }
             if (++s == STAGES) { s = 0; sph ^= 1; }
         }
@@ -323,7 +273,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_tc_kernel(const __grid
         }
     }
     __syncthreads();
-    if (CL) cluster_sync();                       // no CTA leaves while a peer may still store into it / arrive on its barriers
     if (tr && threadIdx.x == 0) { trow[11] = clock64() - t_begin; trow[12] = nchunks; }
     if (warp == 1) {
         tc_fence_after();
@@ -333,25 +282,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_tc_kernel(const __grid
 
 constexpr int SMEM_LIMIT = 227 * 1024;
 
-template <int KW, bool CL>
+template <int KW>
 static int launch(const CUtensorMap& gmap, const CUtensorMap& xmap, Params& p, dim3 grid, cudaStream_t st) {
     using C = Cfg<KW>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel<KW, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
         if (e != cudaSuccess) return fail(SG2_ELAUNCH, "conv_wgrad_tc: cannot opt in to %d B of shared memory: %s", SMEM_LIMIT, cudaGetErrorString(e));
         configured = true;
     }
     p.fstages = FSTAGES;
     while (p.fstages > 2 && C::smem(p.xb, p.fstages) > SMEM_LIMIT) --p.fstages;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = (size_t)C::smem(p.xb, p.fstages); cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL ? 3 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_wgrad_tc_kernel<KW, CL>, gmap, xmap, (const Params)p);
-    if (e != cudaSuccess) return fail(SG2_ELAUNCH, "conv_wgrad_tc: launch: %s", cudaGetErrorString(e));
+    conv_wgrad_tc_kernel<KW><<<grid, NTHREADS, C::smem(p.xb, p.fstages), st>>>(gmap, xmap, p);
     return launched("conv_wgrad_tc");
 }
 
@@ -393,14 +335,8 @@ int conv_wgrad_tc(WgradParams wp, int accumulate, cudaStream_t st) {
     p.chunks_per_split = (p.total_chunks + splits - 1) / splits;
     splits = (p.total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
     dim3 grid((unsigned)tiles, (unsigned)splits);
-    if (wp.k == 3) {
-        // SG2_WGRAD_CLUSTER=0 keeps the three kernel-row CTAs independent (the pre-cluster kernel, kept as a cross-check)
-        static int use_cluster = -1;
-        if (use_cluster < 0) { const char* e = getenv("SG2_WGRAD_CLUSTER"); use_cluster = e ? atoi(e) != 0 : 1; }
-        if (use_cluster) return wg::launch<3, true>(gmap, xmap, p, grid, st);
-        return wg::launch<3, false>(gmap, xmap, p, grid, st);
-    }
-    return wg::launch<1, false>(gmap, xmap, p, grid, st);
+    if (wp.k == 3) return wg::launch<3>(gmap, xmap, p, grid, st);
+    return wg::launch<1>(gmap, xmap, p, grid, st);
 }
 
 }  // namespace sg2
