@@ -10,13 +10,18 @@
 //   MMA      tap (dy,dx), K chunk pair kq: A descriptor start = plane + 2kq*LBO + ((dy+p)*PW + dx+p)*16, SBO = PW*16
 //            (an 8-pixel tile row is an 8-row core-matrix group, consecutive tile rows are PW patch rows apart), so
 //            all taps read the same converted patch; B = pre-packed weight tile of (tap, channel block), SWIZZLE_128B.
-// PRECISE = false: bf16x3 (hi/lo planes, kind::f16, 64 channels per block)           -> data gradients
+//            per (tap, k16) TWO instructions: A0 x [B0 ; B1] (N = 2 BN, the two weight planes are adjacent rows) fills the
+//            accumulator halves [A0*B0 | A0*B1]; A1 x B0 (N = BN) adds into the upper half -- the three split products with
+//            A fetched from shared memory twice instead of three times (the operand fetch paces the MMAs of this kernel)
+// PRECISE = false: bf16x3 (hi/lo planes, kind::f16, 64 channels per block); result = lower + upper half -> data gradients
 // PRECISE = true : fp16x3 + promotion: big = rn_f16(v), small = rn_f16((v - big) * 2^11) (22 mantissa bits together, like
-//                  the tf32 pair of conv_tc32.cu but at the fp16 MMA rate); D1 += big*big and D2 += small*big + big*small
-//                  in separate TMEM accumulators, promoted to fp32 registers (acc += D1 + 2^-11 D2) every 2 taps
-//                  = 8 chained big*big MMAs                                             -> forward convs, fp32-class
+//                  the tf32 pair of conv_tc32.cu but at the fp16 MMA rate); lower half D1 = big*big, upper half D2 =
+//                  big*small + small*big; every `promo_taps` taps (default 2 = 8 chained big*big MMAs -- the tensor core
+//                  truncates its accumulator per MMA) the segment is promoted into fp32 registers (acc += D1 + 2^-11 D2)
+//                  and its TMEM buffer handed back at once                              -> forward convs, fp32-class
 //                  (fp16 range: operands saturate at +-65504; forward activations and weights of this path are O(1))
-// Persistent CTAs (one per SM), double-buffered planes and TMEM accumulators, dedicated epilogue warps.
+// Persistent CTAs (one per SM), double-buffered planes, up to 4 TMEM accumulator buffers, dedicated epilogue warps; edge
+// tiles of ragged images are masked in the epilogue (TMA zero-fills what hangs over the image).
 // Warp roles: 0 patch TMA, 1 MMA (+TMEM alloc), 2..9 transform, 10.. epilogue/promotion, last = weight TMA.
 #include <stdlib.h>
 #include "tc_common.cuh"
@@ -27,10 +32,8 @@ namespace halo {
 using namespace tc;
 
 constexpr int TW = 8, TH = 16, BM = 128;
-constexpr int SLOT = 23 * 1024 + 512;      // one fp32 box: up to 180 rows x 128 B = 23040 B, padded to a 1024 multiple + slack
 constexpr int SLOT_BYTES = 24 * 1024;      // 1024-aligned slot pitch
 constexpr int MAX_ROWS = (TW + 2) * (TH + 2);            // 180 patch rows
-constexpr int PLANE = 8 * MAX_ROWS * 16;                 // 8 chunks x rows x 16 B = 23040 B
 constexpr int PLANE_PITCH = 23 * 1024;                   // 23552
 
 template <int BN, bool PRECISE> struct Cfg {

@@ -42,9 +42,9 @@ class _timed:
 
 
 def set_default_impl(impl: int) -> None:
-    """0 = auto (tcgen05 where the shape allows -- fp32-class tf32x3 for forward convs, bf16x3 for gradients; halo
+    """0 = auto (tcgen05 where the shape allows -- fp32-class split operands for forward convs, bf16x3 for gradients; halo
     kernels where the image tiles by 8x16 -- else fp32 SIMT), 1 = SIMT everywhere, 2..5 = prefer that tcgen05 kernel
-    (per-tap bf16x3 / per-tap tf32x3 / halo bf16x3 / halo tf32x3) wherever it applies."""
+    (per-tap bf16x3 / per-tap tf32x3 + promotion / halo bf16x3 / halo fp16x3 + promotion) wherever it applies."""
     global _default_impl
     assert impl in (0, 1, 2, 3, 4, 5)
     _default_impl = impl
@@ -84,7 +84,7 @@ def _conv_raw(x, w, coef, transpose, in_scale=None, out_scale=None, bias=None, n
     """One library call: y = act(out_scale * conv(x * in_scale, w*coef) + bias + noise).
 
     transpose=True runs the data-gradient conv (x has w.shape[0] channels, y has w.shape[1]).
-    precise: fp32-class tensor-core kernel (tf32x3 + promotion) instead of bf16x3.  Default: yes for forward
+    precise: fp32-class tensor-core kernel (big/small split + promotion) instead of bf16x3.  Default: yes for forward
     convolutions (their outputs decide leaky-ReLU signs), no for data gradients."""
     strict = impl is not None                      # an explicit request must be honoured or fail loudly
     impl = _default_impl if impl is None else impl
