@@ -222,35 +222,83 @@ __global__ void __launch_bounds__(256) upfirdn2d_ring_kernel(UpfirdnParams p) {
 #pragma unroll
     for (int b = 0; b < WW; ++b) colok[b] = (unsigned)(ix0 + b) < (unsigned)p.in_w;
     const float* xc = x + (ptrdiff_t)ix0 * xcol;
-    V ring[FH][WW];
-    auto load_row = [&](int k, V (&dst)[WW]) {     // input row iy0 + k
-        const int iy = iy0 + k;
-        const bool rowok = (unsigned)iy < (unsigned)p.in_h;
-        const float* xr = xc + (ptrdiff_t)iy * xrow;
+    if constexpr (DOWN > 1 && NHWC) {
+        // Input-stationary ring: the FH x WW input window lives in registers, going one output row down loads DOWN new
+        // rows.  Measured on B200 (U4, fraction of HBM peak, this ring | the output-stationary walk below): NHWC down 2
+        // 0.86 | 0.81, NHWC filter 0.59 | 0.64, NCHW down 2 0.65 | 0.74, NCHW filter 0.49 | 0.56 -- hence this condition.
+        V ring[FH][WW];
+        auto load_row = [&](int k, V (&dst)[WW]) {     // input row iy0 + k
+            const int iy = iy0 + k;
+            const bool rowok = (unsigned)iy < (unsigned)p.in_h;
+            const float* xr = xc + (ptrdiff_t)iy * xrow;
 #pragma unroll
-        for (int b = 0; b < WW; ++b) dst[b] = (rowok && colok[b]) ? R::ld(xr + (ptrdiff_t)b * xcol) : R::zero();
-    };
+            for (int b = 0; b < WW; ++b) dst[b] = (rowok && colok[b]) ? R::ld(xr + (ptrdiff_t)b * xcol) : R::zero();
+        };
 #pragma unroll
-    for (int k = 0; k < FH - DOWN; ++k) load_row(k, ring[k % FH]);
+        for (int k = 0; k < FH - DOWN; ++k) load_row(k, ring[k % FH]);
 #pragma unroll
-    for (int s = 0; s < STRIP; ++s) {
+        for (int s = 0; s < STRIP; ++s) {
 #pragma unroll
-        for (int k = FH - DOWN; k < FH; ++k) load_row(s * DOWN + k, ring[(s * DOWN + k) % FH]);
+            for (int k = FH - DOWN; k < FH; ++k) load_row(s * DOWN + k, ring[(s * DOWN + k) % FH]);
 #pragma unroll
-        for (int e = 0; e < COLS; ++e) {
-            V acc = R::zero();
+            for (int e = 0; e < COLS; ++e) {
+                V acc = R::zero();
 #pragma unroll
-            for (int a = 0; a < FH; ++a)
+                for (int a = 0; a < FH; ++a)
 #pragma unroll
-                for (int b = 0; b < FW; ++b) R::fma(acc, wt[a][b], ring[(s * DOWN + a) % FH][e * DOWN + b]);
-            if (jy0 + s < p.out_h && jx + e < p.out_w) R::st(y + (size_t)(jy0 + s) * yrow + (size_t)(jx + e) * ycol, acc);
+                    for (int b = 0; b < FW; ++b) R::fma(acc, wt[a][b], ring[(s * DOWN + a) % FH][e * DOWN + b]);
+                if (jy0 + s < p.out_h && jx + e < p.out_w) R::st(y + (size_t)(jy0 + s) * yrow + (size_t)(jx + e) * ycol, acc);
+            }
+        }
+        return;
+    }
+    // Output-stationary walk: an input row is loaded once (WW values, transient) and scattered into the NA = ceil(FH/DOWN)
+    // output rows it contributes to; an output row is stored when its last input row has passed.  The ring holds
+    // accumulators (NA x COLS values) instead of the FH x WW input window, so a thread needs ~50 registers instead of
+    // ~80: more threads per SM and room for the compiler to issue the next rows' loads early -- the kernel is bound by
+    // memory-level parallelism, not by the FMAs.  Fully unrolled: every ring index is a constant.
+    constexpr int NA = (FH + DOWN - 1) / DOWN;
+    constexpr int NROWS = (STRIP - 1) * DOWN + FH;           // input rows a strip touches
+    V acc[NA][COLS];
+#pragma unroll
+    for (int i = 0; i < NA; ++i)
+#pragma unroll
+        for (int e = 0; e < COLS; ++e) acc[i][e] = R::zero();
+#pragma unroll
+    for (int k = 0; k < NROWS; ++k) {
+        V row[WW];
+        {
+            const int iy = iy0 + k;
+            const bool rowok = (unsigned)iy < (unsigned)p.in_h;
+            const float* xr = xc + (ptrdiff_t)iy * xrow;
+#pragma unroll
+            for (int b = 0; b < WW; ++b) row[b] = (rowok && colok[b]) ? R::ld(xr + (ptrdiff_t)b * xcol) : R::zero();
+        }
+#pragma unroll
+        for (int a = 0; a < FH; ++a) {
+            // input row k is tap row a of output row s = (k - a) / DOWN
+            if ((k - a) >= 0 && (k - a) % DOWN == 0 && (k - a) / DOWN < STRIP) {
+                constexpr int dummy = 0; (void)dummy;
+                const int s = (k - a) / DOWN;
+#pragma unroll
+                for (int e = 0; e < COLS; ++e)
+#pragma unroll
+                    for (int b = 0; b < FW; ++b) R::fma(acc[s % NA][e], wt[a][b], row[e * DOWN + b]);
+                if (a == FH - 1) {                           // last tap row of output s: store and recycle the accumulator
+#pragma unroll
+                    for (int e = 0; e < COLS; ++e) {
+                        if (jy0 + s < p.out_h && jx + e < p.out_w) R::st(y + (size_t)(jy0 + s) * yrow + (size_t)(jx + e) * ycol, acc[s % NA][e]);
+                        acc[s % NA][e] = R::zero();
+                    }
+                }
+            }
         }
     }
 }
 
 template <class V, int FH, int FW, int DOWN, int COLS>
 static int launch_ring_cols(const UpfirdnParams& p, cudaStream_t st) {
-    constexpr int STRIP = 16;
+    constexpr int STRIP = 16;       // 32 halves the halo re-read but leaves the 257-row images of U4 with a nearly empty 9th strip: slower
     constexpr bool NHWC = sizeof(V) == 16;
     dim3 grid;
     if (NHWC) grid = dim3((unsigned)ceil_div(p.out_w, 256 / (p.c / 4)), (unsigned)ceil_div(p.out_h, STRIP), (unsigned)p.n);
@@ -265,8 +313,11 @@ static int launch_ring(const UpfirdnParams& p, cudaStream_t st) {
     if constexpr (sizeof(V) == 16) {
         return launch_ring_cols<V, FH, FW, DOWN, 1>(p, st);
     } else {
+        // columns per thread, measured on B200 (U4, NCHW, fraction of HBM peak): filter 1 -> 0.35, 2 -> 0.48, 4 -> 0.56;
+        // down 2: 1 -> 0.54, 2 -> 0.74, 4 -> 0.52.  SG2_UPF_COLS overrides the choice for that sweep.
         static int cols = 0;
-        if (!cols) { const char* e = getenv("SG2_UPF_COLS"); cols = e ? atoi(e) : 2; }     // measured on B200 (U4, NCHW): 1 -> 0.35, 2 -> 0.51, 4 -> 0.48 of HBM peak
+        if (!cols) { const char* e = getenv("SG2_UPF_COLS"); cols = e ? atoi(e) : -1; }
+        if (cols < 0) return DOWN == 1 ? launch_ring_cols<V, FH, FW, DOWN, 4>(p, st) : launch_ring_cols<V, FH, FW, DOWN, 2>(p, st);
         if (cols == 4) return launch_ring_cols<V, FH, FW, DOWN, 4>(p, st);
         if (cols == 2) return launch_ring_cols<V, FH, FW, DOWN, 2>(p, st);
         return launch_ring_cols<V, FH, FW, DOWN, 1>(p, st);
