@@ -177,6 +177,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        # NCCL writes its version / debug lines to stdout by default; stdout carries the ONE JSON line of this script
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         init_distributed('nccl')
     peaks = load_peaks()
     B = args.batch
