@@ -176,9 +176,13 @@ def run_b200(args):
         raise SystemExit('bench.py: no CUDA device and there is no CPU fallback for the product path')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    json_fd = None
     if world > 1:
-        # NCCL writes its version / debug lines to stdout by default; stdout carries the ONE JSON line of this script
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+        # NCCL prints its version banner / debug lines on the C-level stdout; stdout must carry the ONE JSON line of this
+        # script.  Point fd 1 at stderr for the rest of the run and keep the original stdout for the JSON line.
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         init_distributed('nccl')
     peaks = load_peaks()
     B = args.batch
@@ -314,7 +318,10 @@ def run_b200(args):
                             model_tflops=round(value * FLOP_PER_IMG_STEP / 1e12, 2)),
                 clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu_baseline,
                 upfirdn2d=upf)
-    print(json.dumps(line), flush=True)
+    if json_fd is not None:
+        os.write(json_fd, (json.dumps(line) + '\n').encode())
+    else:
+        print(json.dumps(line), flush=True)
     finish()
 
 
