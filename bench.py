@@ -110,7 +110,12 @@ def run_reference(args):
     if rank != 0:
         return
     batch = 4 if args.steps + args.warmup <= 30 else 2
-    ips, sec, cores = cpu_oracle_step_rate(batch, args.steps, args.warmup)
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers: override it)
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count() or 1
+    ips, sec, cores = cpu_oracle_step_rate(batch, args.steps, args.warmup, threads=threads)
     sample = f'oracle port (oracle/sg2_torch.py, plain PyTorch fp32 CPU) of the same step at B={batch} per step, {args.steps} timed steps'
     line = dict(impl='reference', metric='StyleGAN2 256px G+D step images/sec', value=round(ips, 4), unit='images/sec',
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=round(sec * 1e3, 1),
@@ -303,7 +308,7 @@ def run_b200(args):
     upf = upfirdn2d_rates(dev, peaks) if world == 1 else None
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        ips, sec, cores = cpu_oracle_step_rate(4, 2, 1)
+        ips, sec, cores = cpu_oracle_step_rate(4, 2, 1, threads=(len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else None))
         cpu_baseline = dict(value=round(ips, 4), unit='images/sec', cores=cores, kind='port',
                             sample='oracle/sg2_torch.py (plain-PyTorch CPU restatement of the reference step) at B=4: '
                                    f'1 warm-up + 2 timed steps, {sec:.1f} s/step')
