@@ -382,39 +382,42 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
     }
 }
 
-// w[co][ci][k][k] -> per (n-tile, channel block, tap): two planes of [bn rows x 128 B], SWIZZLE_128B, zero beyond ci
+// w[co][ci][k][k] -> per (n-tile, channel block, tap): two planes of [bn rows x 128 B], SWIZZLE_128B, zero beyond ci.
+// One thread = one 16-byte chunk (8 consecutive input channels) of one row in both planes: 128-bit stores.
 __global__ void conv_pack_halo_kernel(const float* __restrict__ w, unsigned char* __restrict__ wp, int co, int ci, int k,
                                       float coef, int transpose, int bn, int nkb, int kbs, int precise) {
     const int cin = transpose ? co : ci, nout_n = transpose ? ci : co;
-    const int kk2 = k * k;
-    const long long total = (long long)(nout_n / bn) * nkb * kk2 * bn * kbs;
+    const int kk2 = k * k, chunks = kbs >> 3;
+    const long long total = (long long)(nout_n / bn) * nkb * kk2 * bn * chunks;
     const size_t btile = (size_t)2 * bn * 128;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int kk = (int)(idx % kbs);
-        long long r = idx / kbs;
+        const int c8 = (int)(idx % chunks);
+        long long r = idx / chunks;
         const int nl = (int)(r % bn); r /= bn;
         const int t = (int)(r % kk2); r /= kk2;
         const int kb = (int)(r % nkb);
         const int nt = (int)(r / nkb);
-        const int kin = kb * kbs + kk, nout = nt * bn + nl;
-        float v = 0.f;
-        if (kin < cin) {
-            const int o = transpose ? kin : nout, i = transpose ? nout : kin, ts = transpose ? kk2 - 1 - t : t;
-            v = w[((long long)o * ci + i) * kk2 + ts] * coef;
+        const int nout = nt * bn + nl, ts = transpose ? kk2 - 1 - t : t;
+        uint32_t p0[4], p1[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float v[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int kin = kb * kbs + c8 * 8 + 2 * e + h;
+                v[h] = 0.f;
+                if (kin < cin) {
+                    const int o = transpose ? kin : nout, i = transpose ? nout : kin;
+                    v[h] = __ldg(w + ((long long)o * ci + i) * kk2 + ts) * coef;
+                }
+            }
+            if (precise) tc::split2_f16(v[0], v[1], p0[e], p1[e]);
+            else tc::split2(v[0], v[1], p0[e], p1[e]);
         }
         unsigned char* tile = wp + (((size_t)nt * nkb + kb) * kk2 + t) * btile;
-        const size_t off = (size_t)nl * 128 + ((((kk * 2) >> 4) ^ (nl & 7)) << 4) + ((kk * 2) & 15);
-        if (precise) {
-            const __half big = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
-            const __half small = __float2half_rn((v - __half2float(big)) * 2048.f);
-            *reinterpret_cast<__half*>(tile + off) = big;
-            *reinterpret_cast<__half*>(tile + (size_t)bn * 128 + off) = small;
-        } else {
-            const __nv_bfloat16 h = __float2bfloat16_rn(v);
-            const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
-            *reinterpret_cast<__nv_bfloat16*>(tile + off) = h;
-            *reinterpret_cast<__nv_bfloat16*>(tile + (size_t)bn * 128 + off) = l;
-        }
+        const size_t off = (size_t)nl * 128 + (size_t)((c8 ^ (nl & 7)) << 4);
+        *reinterpret_cast<uint4*>(tile + off) = make_uint4(p0[0], p0[1], p0[2], p0[3]);
+        *reinterpret_cast<uint4*>(tile + (size_t)bn * 128 + off) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
     }
 }
 
@@ -469,7 +472,7 @@ int conv_pack_halo(const float* w, void* wp, int co, int ci, int k, float coef, 
     if (!bn || cin % 32) return fail(SG2_ENOTSUP, "conv_pack_halo: unsupported shape");
     const int kbs = 64;
     const int nkb = (cin + kbs - 1) / kbs;
-    const long long total = (long long)(cout / bn) * nkb * k * k * bn * kbs;
+    const long long total = (long long)(cout / bn) * nkb * k * k * bn * (kbs / 8);
     const int blocks = (int)std::min<long long>(ceil_div(total, 256), (long long)num_sms() * 8);
     halo::conv_pack_halo_kernel<<<blocks, 256, 0, st>>>(w, (unsigned char*)wp, co, ci, k, coef, transpose, bn, nkb, kbs, precise);
     return launched("conv_pack_halo");
