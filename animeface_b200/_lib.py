@@ -42,10 +42,19 @@ SIGNATURES = {
     'sg2_conv2d_pack_weight': (_int, [_vp, _vp, _int, _int, _int, _f, _int, _int, _vp]),
     'sg2_conv2d_fwd': (_int, [_vp, _vp, _vp, _i64p, _int, _int, _int, _int, _int, _int,
                               _vp, _vp, _vp, _vp, _int, _f, _f, _int, _vp]),
-    'sg2_conv2d_wgrad': (_int, [_vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _f, _vp, _vp, _int, _int, _vp]),
-    'sg2_reduce_hw': (_int, [_vp, _vp, _vp, _int, _int, _int, _vp]),
-    'sg2_scale_reduce_hw': (_int, [_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _vp]),
-    'sg2_modconv_bwd_prep': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _f, _vp]),
+    'sg2_conv2d_wgrad_workspace': (_i64, [_int, _int, _int, _int, _int, _int, _int]),
+    'sg2_conv2d_wgrad': (_int, [_vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _f, _vp, _vp, _int, _int, _vp, _vp]),
+    'sg2_reduce_hw_workspace': (_i64, [_int, _int, _int]),
+    'sg2_reduce_hw': (_int, [_vp, _vp, _vp, _int, _int, _int, _vp, _vp]),
+    'sg2_scale_reduce_hw': (_int, [_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _vp, _vp]),
+    'sg2_modconv_bwd_prep': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _f, _vp, _vp]),
+    'sg2_split_planes': (_int, [_vp, _vp, _vp, _int, _int, _int, _vp]),
+    'sg2_bwd_prep_planes_workspace': (_i64, [_int, _int, _int]),
+    'sg2_bwd_prep_planes': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _f, _vp]),
+    'sg2_conv2d_planes_supported': (_int, [_int, _int, _int, _int, _int, _int, _int]),
+    'sg2_conv2d_fwd_planes': (_int, [_vp, _vp, _vp, _i64p, _int, _int, _int, _int, _int, _int, _vp, _vp, _int, _f, _f, _vp]),
+    'sg2_conv2d_wgrad_planes_workspace': (_i64, [_int, _int, _int, _int, _int, _int]),
+    'sg2_conv2d_wgrad_planes': (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _f, _int, _vp]),
     'sg2_ema_update': (_int, [_vp, _vp, _i64, _f, _vp]),
     'sg2_counter_add': (_int, [_vp, _int, _int, _int, _int, _vp]),
     'sg2_adam_multi': (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _int, _f, _f, _f, _f, _f, _vp]),

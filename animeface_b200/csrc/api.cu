@@ -105,20 +105,76 @@ extern "C" int sg2_conv2d_fwd(const float* x, const void* packed_w, float* y, co
     return conv_fwd_simt(p, st);
 }
 
+static int wgrad_route(const WgradParams& p, int impl, int& use) {
+    const bool wtc = wgrad_tc_supported(p.n, p.h, p.w, p.ci, p.co, p.k);
+    if (impl >= 2 && !wtc) return fail(SG2_ENOTSUP, "conv2d_wgrad: tcgen05 path does not take this shape");
+    use = impl == 1 ? 1 : (wtc ? 2 : 1);
+    return SG2_OK;
+}
+
+extern "C" int64_t sg2_conv2d_wgrad_workspace(int n, int h, int w, int ci, int co, int k, int impl) {
+    if (n <= 0 || h <= 0 || w <= 0 || ci <= 0 || co <= 0 || (k != 1 && k != 3)) return -1;
+    WgradParams p{};
+    p.n = n; p.h = h; p.w = w; p.ci = ci; p.co = co; p.k = k;
+    p.x = p.gy = (const float*)16;                       // alignment probes of the planners only
+    int use;
+    if (wgrad_route(p, impl, use)) return -1;
+    const int parts = use >= 2 ? wgrad_parts_tc(p) : wgrad_parts_simt(p);
+    return (int64_t)std::max(parts, 1) * co * ci * k * k * (int64_t)sizeof(float);
+}
+
 extern "C" int sg2_conv2d_wgrad(const float* x, const float* gy, float* dw,
                                 int n, int h, int w, int ci, int co, int k, float coef,
                                 const float* in_scale, const float* out_scale,
-                                int accumulate, int impl, sg2_stream_t stream) {
+                                int accumulate, int impl, void* workspace, sg2_stream_t stream) {
     SG2_REQUIRE(x && gy && dw, "conv2d_wgrad: null pointer");
     SG2_REQUIRE(n > 0 && h > 0 && w > 0 && ci > 0 && co > 0, "conv2d_wgrad: empty tensor");
     SG2_REQUIRE(k == 1 || k == 3, "conv2d_wgrad: kernel size %d not supported (1 or 3)", k);
     WgradParams p;
     p.x = x; p.gy = gy; p.dw = dw; p.n = n; p.h = h; p.w = w; p.ci = ci; p.co = co; p.k = k;
-    p.coef = coef; p.in_scale = in_scale; p.out_scale = out_scale; p.chunk = 0;
-    const bool wtc = wgrad_tc_supported(n, h, w, ci, co, k);
-    if (impl >= 2 && !wtc) return fail(SG2_ENOTSUP, "conv2d_wgrad: tcgen05 path does not take this shape");
-    const int use = impl == 1 ? 1 : (wtc ? 2 : 1);
+    p.coef = coef; p.in_scale = in_scale; p.out_scale = out_scale; p.chunk = 0; p.ws = (float*)workspace;
+    int use;
+    int rc = wgrad_route(p, impl, use);
+    if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (use >= 2) return conv_wgrad_tc(p, accumulate, st);
-    return conv_wgrad_simt(p, accumulate, st);
+    const int parts = !workspace ? 0 : (use >= 2 ? wgrad_parts_tc(p) : wgrad_parts_simt(p));
+    rc = use >= 2 ? conv_wgrad_tc(p, accumulate, st) : conv_wgrad_simt(p, accumulate, st);
+    if (rc || !workspace) return rc;
+    return wgrad_sum_parts(p.ws, dw, (long long)co * ci * k * k, parts, accumulate, st);
+}
+
+// ---- bf16 pair-planes entry points (first-order backward fast path) ----------------------------------------------------
+extern "C" int sg2_conv2d_planes_supported(int n, int h, int w, int ci, int co, int k, int wgrad) {
+    if (n <= 0 || h <= 0 || w <= 0 || ci <= 0 || co <= 0 || (k != 1 && k != 3)) return 0;
+    return (wgrad ? wgrad_pl_supported(n, h, w, ci, co, k) : conv_halo_pl_supported(n, h, w, ci, co, k)) ? 1 : 0;
+}
+
+extern "C" int sg2_conv2d_fwd_planes(const void* x_planes, const void* packed_w, float* y, const int64_t y_strides[4],
+                                     int n, int h, int w, int ci, int co, int k,
+                                     const float* out_scale, const float* bias, int act, float alpha, float gain,
+                                     sg2_stream_t stream) {
+    SG2_REQUIRE(x_planes && packed_w && y, "conv2d_fwd_planes: null pointer");
+    SG2_REQUIRE(n > 0 && h > 0 && w > 0 && ci > 0 && co > 0, "conv2d_fwd_planes: empty tensor");
+    SG2_REQUIRE(k == 1 || k == 3, "conv2d_fwd_planes: kernel size %d not supported (1 or 3)", k);
+    SG2_REQUIRE(act == 1 || act == 3, "conv2d_fwd_planes: act must be 1 (linear) or 3 (lrelu)");
+    if (!conv_halo_pl_supported(n, h, w, ci, co, k)) return fail(SG2_ENOTSUP, "conv2d_fwd_planes: no planes kernel for n=%d h=%d w=%d ci=%d co=%d k=%d", n, h, w, ci, co, k);
+    ConvParams p;
+    p.x = nullptr; p.wp = (const char*)packed_w + 256; p.y = y;
+    for (int i = 0; i < 4; ++i) p.ys[i] = y_strides[i];
+    p.n = n; p.h = h; p.w = w; p.ci = ci; p.co = co; p.k = k;
+    p.in_scale = nullptr; p.out_scale = out_scale; p.bias = bias; p.noise = nullptr;
+    p.act = act; p.alpha = alpha; p.gain = gain;
+    return conv_fwd_halo_pl(x_planes, p, (cudaStream_t)stream);
+}
+
+extern "C" int64_t sg2_conv2d_wgrad_planes_workspace(int n, int h, int w, int ci, int co, int k) {
+    if (n <= 0 || h <= 0 || w <= 0 || ci <= 0 || co <= 0) return -1;
+    return wgrad_pl_workspace_bytes(n, h, w, ci, co, k);
+}
+
+extern "C" int sg2_conv2d_wgrad_planes(const void* x_planes, const void* gy_planes, float* dw, void* workspace,
+                                       int n, int h, int w, int ci, int co, int k, float coef, int accumulate, sg2_stream_t stream) {
+    SG2_REQUIRE(x_planes && gy_planes && dw && workspace, "conv2d_wgrad_planes: null pointer");
+    SG2_REQUIRE(n > 0 && h > 0 && w > 0 && ci > 0 && co > 0, "conv2d_wgrad_planes: empty tensor");
+    return conv_wgrad_pl(x_planes, gy_planes, dw, workspace, n, h, w, ci, co, k, coef, accumulate, (cudaStream_t)stream);
 }

@@ -1,0 +1,264 @@
+// tcgen05 implicit-GEMM convolution on a bf16 pair-planes input ("halo" tiling, bf16x3): TMA -> tensor core, no transform.
+//
+// The data-gradient convolutions of the first-order backward pass (convolution_backward behind
+// implementations/StyleGAN2/model.py:129, 44-53; composed like thirdparty/stylegan3_ops/ops/conv2d_gradfix.py:99-145) take the
+// output gradient as pair planes (planes.cu: written by the leaky-ReLU-gradient pass that touches gy anyway).  Compared with
+// conv_halo.cu<PRECISE = false>, which loads an fp32 patch and converts it with 8 transform warps, a pipeline stage here is two
+// TMA boxes [64 ch, 8 + 2p, 16 + 2p, 1] (hi and lo plane; OOB -> 0 = zero padding) landing as K-major SWIZZLE_128B rows, one
+// 128-byte row per patch pixel.  The k*k taps are the SAME tile read through descriptors whose start address is shifted by
+// (dy * PW + dx) rows and whose 8-row groups are PW rows apart: tcgen05 applies the 128-byte swizzle on absolute shared-memory
+// addresses, so any row-shifted start and any group stride read correctly (scripts/exp_umma_shift.cu,
+// profiles/r2a_umma_shift.txt).  MMA scheme, weight tiles, accumulators and epilogue are those of conv_halo.cu:
+//   per (tap, k16): [hi*hi | hi*lo] += A_hi x [B_hi ; B_lo] (N = 2 BN),  upper half += A_lo x B_hi;  result = lower + upper.
+// Warp roles: 0 patch TMA, 1 MMA (+TMEM alloc), 2..5 epilogue, 6 weight TMA.
+#include <cuda_bf16.h>
+#include "tc_common.cuh"
+#include "conv.h"
+
+namespace sg2 {
+namespace halopl {
+using namespace tc;
+
+constexpr int TW = 8, TH = 16, BM = 128;
+constexpr int PLANE_PITCH = 23 * 1024;                  // 180 patch rows x 128 B = 23040, 1024-aligned pitch
+constexpr int NTHREADS = 7 * 32;
+
+template <int BN> struct Cfg {
+    static constexpr int BTILE = 2 * BN * 128;
+    static constexpr int PSTAGES = BN == 128 ? 2 : 3;                       // patch stages (2 planes each)
+    static constexpr int BSTAGES = BN == 128 ? 4 : (BN == 64 ? 5 : 6);
+    static constexpr int SMEM = 1024 + PSTAGES * 2 * PLANE_PITCH + BSTAGES * BTILE + 256;
+    static constexpr int ACC_COLS = 2 * BN;
+    static constexpr int NACC = 512 / ACC_COLS >= 4 ? 4 : 512 / ACC_COLS;
+    static constexpr uint32_t TMEM_COLS = NACC * ACC_COLS;
+};
+
+struct Params {
+    const float* out_scale; const float* bias;
+    float* y;
+    long long ys[4];
+    const unsigned char* wp;
+    int n, h, w, ci, co, k;
+    int tiles_x, tiles_y, m_tiles, n_tiles;
+    int nkb;
+    int act;
+    float alpha, gain;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1) conv_halo_pl_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
+    using C = Cfg<BN>;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t plane_base = base;                                          // [stage][plane]
+    const uint32_t b_base = plane_base + C::PSTAGES * 2 * PLANE_PITCH;
+    const uint32_t bar_base = b_base + C::BSTAGES * C::BTILE;
+    auto pl_full = [&](int s) { return bar_base + 8u * s; };                   // <= 4
+    auto pl_empty = [&](int s) { return bar_base + 32u + 8u * s; };
+    auto b_full = [&](int s) { return bar_base + 64u + 8u * s; };              // <= 6
+    auto b_empty = [&](int s) { return bar_base + 112u + 8u * s; };
+    auto acc_full = [&](int b) { return bar_base + 160u + 8u * b; };           // <= 4
+    auto acc_empty = [&](int b) { return bar_base + 192u + 8u * b; };
+    const uint32_t tmem_slot = bar_base + 224u;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pad = p.k >> 1, taps = p.k * p.k;
+    const int PW = TW + 2 * pad, PH = TH + 2 * pad, PR = PW * PH;
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    auto tile_coords = [&](int tile, int& x0, int& y0, int& b0, int& n0) {
+        const int nt = tile / p.m_tiles, mt = tile % p.m_tiles;
+        x0 = (mt % p.tiles_x) * TW;
+        y0 = ((mt / p.tiles_x) % p.tiles_y) * TH;
+        b0 = mt / (p.tiles_x * p.tiles_y);
+        n0 = nt * BN;
+    };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::PSTAGES; ++s) { mbar_init(pl_full(s), 1); mbar_init(pl_empty(s), 1); }
+        for (int s = 0; s < C::NACC; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 4); }
+        for (int s = 0; s < C::BSTAGES; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_d;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_d) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ================= patch producer: two TMA boxes (hi, lo plane) per (tile, 64-channel block) =================
+        if (elect_one()) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+            int kbg = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int x0, y0, b0, n0;
+                tile_coords(tile, x0, y0, b0, n0);
+                for (int kb = 0; kb < p.nkb; ++kb, ++kbg) {
+                    const int s = kbg % C::PSTAGES;
+                    mbar_wait(pl_empty(s), ((kbg / C::PSTAGES) & 1) ^ 1);
+                    mbar_expect_tx(pl_full(s), (uint32_t)PR * 128u * 2u);
+                    const uint32_t dst = plane_base + (uint32_t)(s * 2) * PLANE_PITCH;
+                    tma_load_5d(dst, &xmap, pl_full(s), kb * 64, x0 - pad, y0 - pad, b0, 0);
+                    tma_load_5d(dst + PLANE_PITCH, &xmap, pl_full(s), kb * 64, x0 - pad, y0 - pad, b0, 1);
+                }
+            }
+        }
+    } else if (warp == 6) {
+        // ================= weight producer: one pre-packed tile per (tile, channel block, tap) =================
+        if (elect_one()) {
+            int bt = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = tile / p.m_tiles;
+                const unsigned char* wsrc = p.wp + (size_t)nt * p.nkb * taps * C::BTILE;
+                for (int i = 0; i < p.nkb * taps; ++i, ++bt) {
+                    const int s = bt % C::BSTAGES;
+                    mbar_wait(b_empty(s), ((bt / C::BSTAGES) & 1) ^ 1);
+                    mbar_expect_tx(b_full(s), C::BTILE);
+                    bulk_load(b_base + s * C::BTILE, wsrc + (size_t)i * C::BTILE, C::BTILE, b_full(s));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (elect_one()) {
+            constexpr uint32_t idesc = idesc_bf16(BM, BN), idesc2 = idesc_bf16(BM, 2 * BN);
+            const uint32_t SBO = (uint32_t)PW * 128u;
+            int bt = 0, kbg = 0, sg = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++sg) {
+                const int abuf = sg % C::NACC;
+                mbar_wait(acc_empty(abuf), ((sg / C::NACC) & 1) ^ 1);
+                const uint32_t d = tmem_d + (uint32_t)(abuf * C::ACC_COLS);
+                for (int kb = 0; kb < p.nkb; ++kb, ++kbg) {
+                    const int ps = kbg % C::PSTAGES;
+                    mbar_wait(pl_full(ps), (kbg / C::PSTAGES) & 1);
+                    const uint32_t pl0 = plane_base + (uint32_t)(ps * 2) * PLANE_PITCH, pl1 = pl0 + PLANE_PITCH;
+                    for (int t = 0, dy = 0, dx = 0; t < taps; ++t, ++bt, dx = (dx + 1 == p.k ? 0 : dx + 1), dy += (dx == 0)) {
+                        const int s = bt % C::BSTAGES;
+                        mbar_wait(b_full(s), (bt / C::BSTAGES) & 1);
+                        tc_fence_after();
+                        const uint32_t arow = (uint32_t)(dy * PW + dx) * 128u;
+                        const uint32_t b0_ = b_base + s * C::BTILE;
+#pragma unroll
+                        for (int kq = 0; kq < 4; ++kq) {
+                            const uint64_t da0 = kmajor_desc_sbo(pl0 + arow + kq * 32, SBO), da1 = kmajor_desc_sbo(pl1 + arow + kq * 32, SBO);
+                            const uint64_t db = kmajor_desc(b0_ + kq * 32);
+                            mma_bf16(d, da0, db, idesc2, !(kb == 0 && t == 0 && kq == 0));     // [hi*hi | hi*lo] += A_hi * [B_hi ; B_lo]
+                            mma_bf16(d + BN, da1, db, idesc, 1);                               //          upper  += A_lo * B_hi
+                        }
+                        mma_commit(b_empty(s));
+                    }
+                    mma_commit(pl_empty(ps));
+                }
+                mma_commit(acc_full(abuf));
+            }
+        }
+    } else if (warp >= 2 && warp < 6) {
+        // ================= epilogue warps =================
+        const int q4 = warp & 3;
+        const int er = q4 * 32 + lane;                    // accumulator row = pixel (y*8 + x)
+        int sg = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++sg) {
+            int x0, y0, b0, n0;
+            tile_coords(tile, x0, y0, b0, n0);
+            const int ex = x0 + (er & 7), ey = y0 + (er >> 3);
+            const bool inside = ex < p.w && ey < p.h;
+            float* yrow = p.y + (long long)b0 * p.ys[0] + (long long)ey * p.ys[2] + (long long)ex * p.ys[3];
+            const float* osc = p.out_scale ? p.out_scale + (long long)b0 * p.co + n0 : nullptr;
+            const float* bsp = p.bias ? p.bias + n0 : nullptr;
+            const uint32_t lane_addr = tmem_d + ((uint32_t)(q4 * 32) << 16);
+            const int abuf = sg % C::NACC;
+            mbar_wait(acc_full(abuf), (sg / C::NACC) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < BN / 16; ++c) {
+                uint32_t v[16], v2[16];
+                const uint32_t col = (uint32_t)(abuf * C::ACC_COLS + c * 16);
+                tmem_ld16_async(lane_addr + col, v);
+                tmem_ld16_async(lane_addr + col + BN, v2);
+                tmem_ld_wait();
+                reg_fence(v); reg_fence(v2);
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    float o[4] = {__uint_as_float(v[j]) + __uint_as_float(v2[j]), __uint_as_float(v[j + 1]) + __uint_as_float(v2[j + 1]),
+                                  __uint_as_float(v[j + 2]) + __uint_as_float(v2[j + 2]), __uint_as_float(v[j + 3]) + __uint_as_float(v2[j + 3])};
+                    const int cbase = c * 16 + j;
+                    if (osc) { const float4 t = ldg4(osc + cbase); o[0] *= t.x; o[1] *= t.y; o[2] *= t.z; o[3] *= t.w; }
+                    if (bsp) { const float4 t = ldg4(bsp + cbase); o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w; }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float val = o[e];
+                        if (p.act == 3) val = val > 0.f ? val : val * p.alpha;
+                        o[e] = val * p.gain;
+                    }
+                    if (inside) {
+                        const int cb = n0 + cbase;
+                        if (p.ys[1] == 1) st4(yrow + cb, make_float4(o[0], o[1], o[2], o[3]));
+                        else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) yrow[(long long)(cb + e) * p.ys[1]] = o[e];
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty(abuf));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_d, C::TMEM_COLS);
+    }
+}
+
+static int pick_bn(int co) { return co % 128 == 0 ? 128 : (co == 64 ? 64 : (co == 32 ? 32 : 0)); }
+
+template <int BN>
+static int launch(const CUtensorMap& map, const Params& tp, dim3 grid, cudaStream_t st) {
+    using C = Cfg<BN>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_halo_pl_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e != cudaSuccess) return fail(SG2_ELAUNCH, "conv_halo_pl: cannot opt in to %d B of shared memory: %s", C::SMEM, cudaGetErrorString(e));
+        configured = true;
+    }
+    conv_halo_pl_kernel<BN><<<grid, NTHREADS, C::SMEM, st>>>(map, tp);
+    return launched("conv_halo_pl");
+}
+
+}  // namespace halopl
+
+// ci = channels of the planes input (a multiple of 64: one 128-byte row per pixel), co as conv_halo.cu
+bool conv_halo_pl_supported(int n, int h, int w, int ci, int co, int k) {
+    if (ci % 64 != 0) return false;
+    return conv_halo_supported(n, h, w, ci, co, k);
+}
+
+int conv_fwd_halo_pl(const void* x_planes, const ConvParams& p, cudaStream_t st) {
+    if (!conv_halo_pl_supported(p.n, p.h, p.w, p.ci, p.co, p.k)) return fail(SG2_ENOTSUP, "conv_fwd_halo_pl: unsupported shape");
+    const int pad = p.k >> 1;
+    CUtensorMap map;
+    int rc = tc::make_planes_map(&map, x_planes, p.n, p.h, p.w, p.ci, halopl::TW + 2 * pad, halopl::TH + 2 * pad, 1, "conv_fwd_halo_pl");
+    if (rc) return rc;
+    halopl::Params tp;
+    tp.out_scale = p.out_scale; tp.bias = p.bias;
+    tp.y = p.y;
+    for (int i = 0; i < 4; ++i) tp.ys[i] = p.ys[i];
+    tp.wp = (const unsigned char*)p.wp;
+    tp.n = p.n; tp.h = p.h; tp.w = p.w; tp.ci = p.ci; tp.co = p.co; tp.k = p.k;
+    tp.tiles_x = (p.w + halopl::TW - 1) / halopl::TW; tp.tiles_y = (p.h + halopl::TH - 1) / halopl::TH;
+    tp.m_tiles = tp.tiles_x * tp.tiles_y * p.n;
+    const int bn = halopl::pick_bn(p.co);
+    tp.n_tiles = p.co / bn;
+    tp.nkb = p.ci / 64;
+    tp.act = p.act; tp.alpha = p.alpha; tp.gain = p.gain;
+    dim3 grid((unsigned)std::min(tp.m_tiles * tp.n_tiles, num_sms()));
+    if (bn == 128) return halopl::launch<128>(map, tp, grid, st);
+    if (bn == 64) return halopl::launch<64>(map, tp, grid, st);
+    return halopl::launch<32>(map, tp, grid, st);
+}
+
+}  // namespace sg2

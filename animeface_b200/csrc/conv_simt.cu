@@ -257,7 +257,11 @@ __global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(WgradParams p) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int co = n0 + tx * 4 + j;
-            if (co < p.co) atomicAdd(p.dw + ((long long)co * p.ci + ci) * kk2 + t, acc[i][j] * p.coef);
+            if (co < p.co) {
+                const long long o = ((long long)co * p.ci + ci) * kk2 + t;
+                if (p.ws) p.ws[(long long)blockIdx.z * ((long long)p.co * p.ci * kk2) + o] = acc[i][j] * p.coef;
+                else atomicAdd(p.dw + o, acc[i][j] * p.coef);
+            }
         }
     }
 }
@@ -298,10 +302,42 @@ int conv_fwd_simt(const ConvParams& p, cudaStream_t st) {
     return launched("conv_fwd_simt");
 }
 
-int conv_wgrad_simt(WgradParams p, int accumulate, cudaStream_t st) {
+static long long simt_wgrad_splits(const WgradParams& p, long long& chunk) {
     const long long P = (long long)p.n * p.h * p.w;
     const int kk2 = p.k * p.k;
-    if (!accumulate) {
+    const int mtiles = (p.ci + 63) / 64, ntiles = (p.co + 63) / 64;
+    const long long tiles = (long long)mtiles * ntiles * kk2;
+    long long want = std::max<long long>(1, (4LL * num_sms()) / tiles);
+    long long splits = std::min<long long>(want, ceil_div(P, 256));
+    splits = std::max<long long>(1, std::min<long long>(splits, 65535));
+    chunk = ceil_div(ceil_div(P, splits), kBK) * kBK;
+    return ceil_div(P, chunk);
+}
+
+int wgrad_parts_simt(const WgradParams& p) {
+    const int thin = wgrad_parts_thin(p);
+    if (thin > 0) return thin;
+    long long chunk;
+    return (int)simt_wgrad_splits(p, chunk);
+}
+
+// dw[i] (+)= sum_parts ws[part][i], parts added in index order
+__global__ void __launch_bounds__(256) wgrad_sum_parts_kernel(const float* __restrict__ ws, float* __restrict__ dw, long long size, int parts, int accumulate) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= size) return;
+    float s = 0.f;
+    for (int k = 0; k < parts; ++k) s += ws[(long long)k * size + i];
+    dw[i] = accumulate ? dw[i] + s : s;
+}
+
+int wgrad_sum_parts(const float* ws, float* dw, long long size, int parts, int accumulate, cudaStream_t st) {
+    wgrad_sum_parts_kernel<<<(unsigned)ceil_div(size, 256), 256, 0, st>>>(ws, dw, size, parts, accumulate);
+    return launched("wgrad_sum_parts");
+}
+
+int conv_wgrad_simt(WgradParams p, int accumulate, cudaStream_t st) {
+    const int kk2 = p.k * p.k;
+    if (!accumulate && !p.ws) {
         cudaError_t e = cudaMemsetAsync(p.dw, 0, sizeof(float) * (size_t)p.co * p.ci * kk2, st);
         if (e != cudaSuccess) return fail(SG2_ELAUNCH, "conv_wgrad: memset: %s", cudaGetErrorString(e));
     }
@@ -310,12 +346,8 @@ int conv_wgrad_simt(WgradParams p, int accumulate, cudaStream_t st) {
         if (rc != SG2_ENOTSUP) return rc;
     }
     const int mtiles = (p.ci + 63) / 64, ntiles = (p.co + 63) / 64;
-    const long long tiles = (long long)mtiles * ntiles * kk2;
-    long long want = std::max<long long>(1, (4LL * num_sms()) / tiles);
-    long long splits = std::min<long long>(want, ceil_div(P, 256));
-    splits = std::max<long long>(1, std::min<long long>(splits, 65535));
-    long long chunk = ceil_div(ceil_div(P, splits), kBK) * kBK;
-    splits = ceil_div(P, chunk);
+    long long chunk;
+    const long long splits = simt_wgrad_splits(p, chunk);
     p.chunk = chunk;
     dim3 grid((unsigned)(mtiles * kk2), (unsigned)ntiles, (unsigned)splits);
     conv_wgrad_simt_kernel<<<grid, 256, 0, st>>>(p);

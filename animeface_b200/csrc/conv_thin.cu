@@ -157,6 +157,7 @@ struct WgParams {
     const float* wide; const float* thin;      // [P, C], [P, T] dense
     const float* wide_scale; const float* thin_scale;   // [n, C], [n, T] or null
     float* dw;
+    float* ws;                                  // per-block partial buffers (deterministic reduction) or null (atomics)
     int n, hw, C, T;
     int thin_is_ci;                             // 1: dw[c_wide][t]  (from_rgb), 0: dw[t][c_wide] (ToImage)
     float coef;
@@ -205,8 +206,9 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(WgParams p) {
         float sc = p.coef;
         if (p.wide_scale) sc *= __ldg(p.wide_scale + (long long)b * p.C + c);
         if (p.thin_scale) sc *= __ldg(p.thin_scale + (long long)b * T + t);
-        float* dst = p.thin_is_ci ? p.dw + (long long)c * T + t : p.dw + (long long)t * p.C + c;
-        atomicAdd(dst, s * sc);
+        const long long el = p.thin_is_ci ? (long long)c * T + t : (long long)t * p.C + c;
+        if (p.ws) p.ws[((long long)blockIdx.y * gridDim.x + blockIdx.x) * ((long long)p.C * T) + el] = s * sc;
+        else atomicAdd(p.dw + el, s * sc);
     }
 }
 
@@ -259,9 +261,8 @@ int conv_fwd_thin(const ConvParams& p, cudaStream_t st) {
     return SG2_ENOTSUP;
 }
 
-int conv_wgrad_thin(const WgradParams& wp, cudaStream_t st) {
-    if (wp.k != 1) return SG2_ENOTSUP;
-    thin::WgParams p;
+static bool thin_wgrad_plan(const WgradParams& wp, thin::WgParams& p, int& splits) {
+    if (wp.k != 1) return false;
     if (wp.ci <= 4 && (wp.co % 4) == 0 && wp.co <= 1024) {
         p.wide = wp.gy; p.thin = wp.x; p.wide_scale = wp.out_scale; p.thin_scale = wp.in_scale;
         p.C = wp.co; p.T = wp.ci; p.thin_is_ci = 1;
@@ -269,15 +270,28 @@ int conv_wgrad_thin(const WgradParams& wp, cudaStream_t st) {
         p.wide = wp.x; p.thin = wp.gy; p.wide_scale = wp.in_scale; p.thin_scale = wp.out_scale;
         p.C = wp.ci; p.T = wp.co; p.thin_is_ci = 0;
     } else {
-        return SG2_ENOTSUP;
+        return false;
     }
-    if (((uintptr_t)p.wide % 16) != 0) return SG2_ENOTSUP;
-    p.dw = wp.dw; p.n = wp.n; p.hw = wp.h * wp.w; p.coef = wp.coef;
+    if (((uintptr_t)p.wide % 16) != 0) return false;
+    p.dw = wp.dw; p.ws = wp.ws; p.n = wp.n; p.hw = wp.h * wp.w; p.coef = wp.coef;
     // enough blocks to fill the machine, at least 64 pixels per pixel slot
     const int nslot = 256 / (p.C / 4) > 0 ? 256 / (p.C / 4) : 1;
-    int splits = std::max(1, std::min((4 * num_sms() + p.n - 1) / p.n, p.hw / (nslot * 16) + 1));
+    splits = std::max(1, std::min((4 * num_sms() + p.n - 1) / p.n, p.hw / (nslot * 16) + 1));
     p.pix_per_block = (p.hw + splits - 1) / splits;
     splits = (p.hw + p.pix_per_block - 1) / p.pix_per_block;
+    return true;
+}
+
+int wgrad_parts_thin(const WgradParams& wp) {
+    thin::WgParams p;
+    int splits;
+    return thin_wgrad_plan(wp, p, splits) ? splits * wp.n : 0;
+}
+
+int conv_wgrad_thin(const WgradParams& wp, cudaStream_t st) {
+    thin::WgParams p;
+    int splits;
+    if (!thin_wgrad_plan(wp, p, splits)) return SG2_ENOTSUP;
     dim3 grid((unsigned)splits, (unsigned)p.n);
     switch (p.T) {
         case 1: thin::thin_wgrad_kernel<1><<<grid, 256, 0, st>>>(p); break;

@@ -8,7 +8,9 @@
 
 namespace sg2 {
 
-__device__ __forceinline__ void block_reduce_store(float4 acc, float (*sh)[68], float* out_row, int c, int cbase) {
+// out_row: the [c] row of this (sample) in the output -- atomics across the hw slices -- or, with `part`, this block's own
+// row in the per-slice partial buffer (plain store; aux_sum_slices_kernel adds the slices in a fixed order)
+__device__ __forceinline__ void block_reduce_store(float4 acc, float (*sh)[68], float* out_row, int c, int cbase, bool part = false) {
     const int q = threadIdx.x & 15, pl = threadIdx.x >> 4;
     sh[pl][q * 4 + 0] = acc.x; sh[pl][q * 4 + 1] = acc.y; sh[pl][q * 4 + 2] = acc.z; sh[pl][q * 4 + 3] = acc.w;
     __syncthreads();
@@ -17,7 +19,7 @@ __device__ __forceinline__ void block_reduce_store(float4 acc, float (*sh)[68], 
 #pragma unroll
         for (int i = 0; i < 16; ++i) s += sh[i][threadIdx.x];
         const int cc = cbase + threadIdx.x;
-        if (cc < c) atomicAdd(out_row + cc, s);
+        if (cc < c) { if (part) out_row[cc] = s; else atomicAdd(out_row + cc, s); }
     }
     __syncthreads();
 }
@@ -25,7 +27,7 @@ __device__ __forceinline__ void block_reduce_store(float4 acc, float (*sh)[68], 
 // out[b,c] += sum_{i in slice} a*bm ; optionally a_out = a * scale[b,c]
 __global__ void __launch_bounds__(256) scale_reduce_hw_kernel(const float* __restrict__ a, const float* __restrict__ bm,
                                                               const float* __restrict__ scale, float* __restrict__ a_out,
-                                                              float* __restrict__ out, int hw, int c, int slice) {
+                                                              float* __restrict__ out, float* __restrict__ part, int n, int hw, int c, int slice) {
     __shared__ float sh[16][68];
     const int q = threadIdx.x & 15, pl = threadIdx.x >> 4;
     const int c0 = blockIdx.x * 64 + q * 4, b = blockIdx.y;
@@ -41,7 +43,8 @@ __global__ void __launch_bounds__(256) scale_reduce_hw_kernel(const float* __res
             acc = add4(acc, bm ? mul4(v, ldg4(bm + base + (long long)i * c)) : v);
         }
     }
-    block_reduce_store(acc, sh, out + (long long)b * c, c, blockIdx.x * 64);
+    if (part) block_reduce_store(acc, sh, part + ((long long)blockIdx.z * n + b) * c, c, blockIdx.x * 64, true);
+    else block_reduce_store(acc, sh, out + (long long)b * c, c, blockIdx.x * 64);
 }
 
 // One pass over (gy, y):  gu = gy * act'(y);  g_acc = gu * d;  gb_part[b,o] += sum gu;
@@ -50,7 +53,7 @@ __global__ void __launch_bounds__(256) modconv_bwd_prep_kernel(const float* __re
                                                                const float* __restrict__ noise, const float* __restrict__ bias,
                                                                const float* __restrict__ d, float* __restrict__ g_acc,
                                                                float* __restrict__ gb_part, float* __restrict__ gd,
-                                                               int hw, int c, int slice, float alpha) {
+                                                               float* __restrict__ part, int n, int hw, int c, int slice, float alpha) {
     __shared__ float sh[16][68];
     const int q = threadIdx.x & 15, pl = threadIdx.x >> 4;
     const int c0 = blockIdx.x * 64 + q * 4, b = blockIdx.y;
@@ -79,8 +82,22 @@ __global__ void __launch_bounds__(256) modconv_bwd_prep_kernel(const float* __re
         }
         if (gd) { sgd.x /= dv.x; sgd.y /= dv.y; sgd.z /= dv.z; sgd.w /= dv.w; }
     }
-    block_reduce_store(sgu, sh, gb_part + (long long)b * c, c, blockIdx.x * 64);
-    if (gd) block_reduce_store(sgd, sh, gd + (long long)b * c, c, blockIdx.x * 64);
+    if (part) {
+        const long long row = ((long long)blockIdx.z * n + b) * c;
+        block_reduce_store(sgu, sh, part + row, c, blockIdx.x * 64, true);
+        if (gd) block_reduce_store(sgd, sh, part + (long long)gridDim.z * n * c + row, c, blockIdx.x * 64, true);
+    } else {
+        block_reduce_store(sgu, sh, gb_part + (long long)b * c, c, blockIdx.x * 64);
+        if (gd) block_reduce_store(sgd, sh, gd + (long long)b * c, c, blockIdx.x * 64);
+    }
+}
+
+__global__ void __launch_bounds__(256) aux_sum_slices_kernel(const float* __restrict__ part, float* __restrict__ out, long long nc, int slices) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= nc) return;
+    float s = 0.f;
+    for (int k = 0; k < slices; ++k) s += part[(long long)k * nc + i];
+    out[i] = s;
 }
 
 static void pick_grid(int n, int hw, int c, dim3& grid, int& slice) {
@@ -96,34 +113,55 @@ static void pick_grid(int n, int hw, int c, dim3& grid, int& slice) {
 
 using namespace sg2;
 
+extern "C" int64_t sg2_reduce_hw_workspace(int n, int hw, int c) {
+    if (n <= 0 || hw <= 0 || c <= 0) return -1;
+    dim3 grid; int slice;
+    pick_grid(n, hw, c, grid, slice);
+    return (int64_t)2 * grid.z * n * c * (int64_t)sizeof(float);
+}
+
+static int sum_slices(const float* part, float* out, long long nc, int slices, cudaStream_t st) {
+    aux_sum_slices_kernel<<<(unsigned)ceil_div(nc, 256), 256, 0, st>>>(part, out, nc, slices);
+    return launched("sum_slices");
+}
+
 extern "C" int sg2_scale_reduce_hw(const float* a, const float* bm, const float* scale, float* a_out, float* out,
-                                   int n, int hw, int c, sg2_stream_t stream) {
+                                   int n, int hw, int c, void* workspace, sg2_stream_t stream) {
     SG2_REQUIRE(a && out, "scale_reduce_hw: null pointer");
     SG2_REQUIRE(n > 0 && hw > 0 && c > 0 && c % 4 == 0, "scale_reduce_hw: need n,hw > 0 and C %% 4 == 0 (C=%d)", c);
     cudaStream_t st = (cudaStream_t)stream;
-    SG2_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n * c, st));
+    if (!workspace) SG2_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n * c, st));
     dim3 grid; int slice;
     pick_grid(n, hw, c, grid, slice);
-    scale_reduce_hw_kernel<<<grid, 256, 0, st>>>(a, bm, scale, a_out, out, hw, c, slice);
-    return launched("scale_reduce_hw");
+    scale_reduce_hw_kernel<<<grid, 256, 0, st>>>(a, bm, scale, a_out, out, (float*)workspace, n, hw, c, slice);
+    int rc = launched("scale_reduce_hw");
+    if (rc || !workspace) return rc;
+    return sum_slices((const float*)workspace, out, (long long)n * c, (int)grid.z, st);
 }
 
-extern "C" int sg2_reduce_hw(const float* a, const float* bm, float* out, int n, int hw, int c, sg2_stream_t stream) {
-    return sg2_scale_reduce_hw(a, bm, nullptr, nullptr, out, n, hw, c, stream);
+extern "C" int sg2_reduce_hw(const float* a, const float* bm, float* out, int n, int hw, int c, void* workspace, sg2_stream_t stream) {
+    return sg2_scale_reduce_hw(a, bm, nullptr, nullptr, out, n, hw, c, workspace, stream);
 }
 
 extern "C" int sg2_modconv_bwd_prep(const float* gy, const float* y, const float* noise, const float* bias,
                                     const float* d, float* g_acc, float* gb_part, float* gd,
-                                    int n, int hw, int c, float alpha, sg2_stream_t stream) {
+                                    int n, int hw, int c, float alpha, void* workspace, sg2_stream_t stream) {
     SG2_REQUIRE(gy && y && g_acc && gb_part, "modconv_bwd_prep: null pointer");
     SG2_REQUIRE(n > 0 && hw > 0 && c > 0 && c % 4 == 0, "modconv_bwd_prep: need n,hw > 0 and C %% 4 == 0 (C=%d)", c);
     SG2_REQUIRE(alpha != 0.f, "modconv_bwd_prep: alpha must be non-zero (the activation is inverted from y)");
     SG2_REQUIRE(!gd || d, "modconv_bwd_prep: gd requested without d");
     cudaStream_t st = (cudaStream_t)stream;
-    SG2_CUDA(cudaMemsetAsync(gb_part, 0, sizeof(float) * (size_t)n * c, st));
-    if (gd) SG2_CUDA(cudaMemsetAsync(gd, 0, sizeof(float) * (size_t)n * c, st));
+    if (!workspace) {
+        SG2_CUDA(cudaMemsetAsync(gb_part, 0, sizeof(float) * (size_t)n * c, st));
+        if (gd) SG2_CUDA(cudaMemsetAsync(gd, 0, sizeof(float) * (size_t)n * c, st));
+    }
     dim3 grid; int slice;
     pick_grid(n, hw, c, grid, slice);
-    modconv_bwd_prep_kernel<<<grid, 256, 0, st>>>(gy, y, noise, bias, d, g_acc, gb_part, gd, hw, c, slice, alpha);
-    return launched("modconv_bwd_prep");
+    modconv_bwd_prep_kernel<<<grid, 256, 0, st>>>(gy, y, noise, bias, d, g_acc, gb_part, gd, (float*)workspace, n, hw, c, slice, alpha);
+    int rc = launched("modconv_bwd_prep");
+    if (rc || !workspace) return rc;
+    const long long nc = (long long)n * c;
+    rc = sum_slices((const float*)workspace, gb_part, nc, (int)grid.z, st);
+    if (rc || !gd) return rc;
+    return sum_slices((const float*)workspace + (long long)grid.z * nc, gd, nc, (int)grid.z, st);
 }

@@ -1,0 +1,162 @@
+// "Pair planes": an fp32 NHWC tensor stored as two bf16 tensors hi = bf16(v), lo = bf16(v - hi), back to back ([2][n][hw][c],
+// 4 bytes per element like the fp32 it replaces).  hi + lo carries 16 mantissa bits; the three (or four) cross products of two
+// such pairs are the bf16x3 arithmetic of the gradient convolutions.  Producing the planes ONCE per tensor, in the
+// elementwise pass that touches the tensor anyway, lets the tcgen05 data-gradient and weight-gradient kernels (conv_halo_pl.cu,
+// wgrad_pl.cu) take their operands by TMA straight into SWIZZLE_128B tiles: no in-kernel fp32 -> bf16 transform, which was the
+// limiter of the round-1 weight-gradient kernel (every CTA of a (kernel row, channel tile) re-converted gy and x).
+//
+//   split_planes_kernel      planes = split(x * scale[b,c])                       (x of a conv, for its weight gradient)
+//   bwd_prep_planes_kernel   the backward prologue of y = lrelu(d*acc + bias + noise) (modconv_aux.cu) with g_acc written as
+//                            planes; per-(sample, channel) sums reduced DETERMINISTICALLY (per-slice partials, fixed order).
+// HBM-bound, 128-bit accesses, grid = (64-channel chunks, samples, hw slices).
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace sg2 {
+
+__device__ __forceinline__ void split4(const float4& v, uint2& hi, uint2& lo) {
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+    const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+    hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+    lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+}
+
+__global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                                           __nv_bfloat16* __restrict__ planes, long long plane_stride, int hw, int c, int slice) {
+    const int q = threadIdx.x & 15, pl = threadIdx.x >> 4;
+    const int c0 = blockIdx.x * 64 + q * 4, b = blockIdx.y;
+    const int beg = blockIdx.z * slice, end = min(hw, beg + slice);
+    if (c0 >= c) return;
+    const long long base = (long long)b * hw * c + c0;
+    const float4 sc = scale ? ldg4(scale + (long long)b * c + c0) : make_float4(1.f, 1.f, 1.f, 1.f);
+    for (int i = beg + pl; i < end; i += 16) {
+        const long long o = base + (long long)i * c;
+        uint2 hi, lo;
+        split4(mul4(ldg4(x + o), sc), hi, lo);
+        *reinterpret_cast<uint2*>(planes + o) = hi;
+        *reinterpret_cast<uint2*>(planes + plane_stride + o) = lo;
+    }
+}
+
+// per-block partial sums -> part[(slice, b, c)] (no atomics: the caller's second pass adds the slices in a fixed order)
+__device__ __forceinline__ void block_reduce_part(float4 acc, float (*sh)[68], float* out_row, int c, int cbase) {
+    const int q = threadIdx.x & 15, pl = threadIdx.x >> 4;
+    sh[pl][q * 4 + 0] = acc.x; sh[pl][q * 4 + 1] = acc.y; sh[pl][q * 4 + 2] = acc.z; sh[pl][q * 4 + 3] = acc.w;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s += sh[i][threadIdx.x];
+        const int cc = cbase + threadIdx.x;
+        if (cc < c) out_row[cc] = s;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) bwd_prep_planes_kernel(const float* __restrict__ gy, const float* __restrict__ y,
+                                                              const float* __restrict__ noise, const float* __restrict__ bias,
+                                                              const float* __restrict__ d, __nv_bfloat16* __restrict__ planes,
+                                                              long long plane_stride, float* __restrict__ part_gb, float* __restrict__ part_gd,
+                                                              int n, int hw, int c, int slice, float alpha) {
+    __shared__ float sh[16][68];
+    const int q = threadIdx.x & 15, pl = threadIdx.x >> 4;
+    const int c0 = blockIdx.x * 64 + q * 4, b = blockIdx.y;
+    const int beg = blockIdx.z * slice, end = min(hw, beg + slice);
+    float4 sgu = f4zero(), sgd = f4zero();
+    if (c0 < c) {
+        const long long base = (long long)b * hw * c + c0;
+        const float4 dv = d ? ldg4(d + (long long)b * c + c0) : make_float4(1.f, 1.f, 1.f, 1.f);
+        const float4 bv = bias ? ldg4(bias + c0) : f4zero();
+        const float inv_alpha = 1.f / alpha;
+        for (int i = beg + pl; i < end; i += 16) {
+            const long long o = base + (long long)i * c;
+            const float4 g = ldg4(gy + o);
+            float4 gu = g, u = f4zero();
+            if (y) {
+                const float4 yv = ldg4(y + o);
+                gu.x = yv.x > 0.f ? g.x : g.x * alpha; u.x = yv.x > 0.f ? yv.x : yv.x * inv_alpha;
+                gu.y = yv.y > 0.f ? g.y : g.y * alpha; u.y = yv.y > 0.f ? yv.y : yv.y * inv_alpha;
+                gu.z = yv.z > 0.f ? g.z : g.z * alpha; u.z = yv.z > 0.f ? yv.z : yv.z * inv_alpha;
+                gu.w = yv.w > 0.f ? g.w : g.w * alpha; u.w = yv.w > 0.f ? yv.w : yv.w * inv_alpha;
+            }
+            uint2 hi, lo;
+            split4(mul4(gu, dv), hi, lo);
+            *reinterpret_cast<uint2*>(planes + o) = hi;
+            *reinterpret_cast<uint2*>(planes + plane_stride + o) = lo;
+            sgu = add4(sgu, gu);
+            if (part_gd) {
+                const float nz = noise ? __ldg(noise + (long long)b * hw + i) : 0.f;
+                sgd.x = fmaf(gu.x, u.x - bv.x - nz, sgd.x); sgd.y = fmaf(gu.y, u.y - bv.y - nz, sgd.y);
+                sgd.z = fmaf(gu.z, u.z - bv.z - nz, sgd.z); sgd.w = fmaf(gu.w, u.w - bv.w - nz, sgd.w);
+            }
+        }
+        if (part_gd) { sgd.x /= dv.x; sgd.y /= dv.y; sgd.z /= dv.z; sgd.w /= dv.w; }
+    }
+    const long long row = ((long long)blockIdx.z * n + b) * c;
+    block_reduce_part(sgu, sh, part_gb + row, c, blockIdx.x * 64);
+    if (part_gd) block_reduce_part(sgd, sh, part_gd + row, c, blockIdx.x * 64);
+}
+
+// out[i] = sum_s part[s][i] in slice order (deterministic); i over n*c
+__global__ void __launch_bounds__(256) sum_slices_kernel(const float* __restrict__ part, float* __restrict__ out, long long nc, int slices) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= nc) return;
+    float s = 0.f;
+    for (int k = 0; k < slices; ++k) s += part[(long long)k * nc + i];
+    out[i] = s;
+}
+
+static void pick_grid_pl(int n, int hw, int c, dim3& grid, int& slice) {
+    const int cchunks = (c + 63) / 64;
+    long long want = std::max<long long>(1, (4LL * num_sms()) / ((long long)cchunks * n));
+    int slices = (int)std::min<long long>(std::min<long long>(want, 64), ceil_div(hw, 64));
+    slice = (int)ceil_div(hw, slices);
+    slices = (int)ceil_div(hw, slice);
+    grid = dim3(cchunks, n, slices);
+}
+
+}  // namespace sg2
+
+using namespace sg2;
+
+extern "C" int sg2_split_planes(const float* x, const float* scale, void* planes, int n, int hw, int c, sg2_stream_t stream) {
+    SG2_REQUIRE(x && planes, "split_planes: null pointer");
+    SG2_REQUIRE(n > 0 && hw > 0 && c > 0 && c % 4 == 0, "split_planes: need n,hw > 0 and C %% 4 == 0 (C=%d)", c);
+    dim3 grid; int slice;
+    pick_grid_pl(n, hw, c, grid, slice);
+    split_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, scale, (__nv_bfloat16*)planes, (long long)n * hw * c, hw, c, slice);
+    return launched("split_planes");
+}
+
+extern "C" int64_t sg2_bwd_prep_planes_workspace(int n, int hw, int c) {
+    if (n <= 0 || hw <= 0 || c <= 0) return -1;
+    dim3 grid; int slice;
+    pick_grid_pl(n, hw, c, grid, slice);
+    return (int64_t)2 * grid.z * n * c * (int64_t)sizeof(float);
+}
+
+extern "C" int sg2_bwd_prep_planes(const float* gy, const float* y, const float* noise, const float* bias, const float* d,
+                                   void* planes, float* gb, float* gd, void* workspace,
+                                   int n, int hw, int c, float alpha, sg2_stream_t stream) {
+    SG2_REQUIRE(gy && planes && gb && workspace, "bwd_prep_planes: null pointer");
+    SG2_REQUIRE(n > 0 && hw > 0 && c > 0 && c % 4 == 0, "bwd_prep_planes: need n,hw > 0 and C %% 4 == 0 (C=%d)", c);
+    SG2_REQUIRE(alpha != 0.f, "bwd_prep_planes: alpha must be non-zero (the activation is inverted from y)");
+    SG2_REQUIRE(!gd || (d && y), "bwd_prep_planes: gd requested without d / y");
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid; int slice;
+    pick_grid_pl(n, hw, c, grid, slice);
+    const long long nc = (long long)n * c;
+    float* part_gb = (float*)workspace;
+    float* part_gd = gd ? part_gb + (long long)grid.z * nc : nullptr;
+    bwd_prep_planes_kernel<<<grid, 256, 0, st>>>(gy, y, noise, bias, d, (__nv_bfloat16*)planes, (long long)n * hw * c, part_gb, part_gd,
+                                                 n, hw, c, slice, alpha);
+    int rc = launched("bwd_prep_planes");
+    if (rc) return rc;
+    const int blocks = (int)ceil_div(nc, 256);
+    sum_slices_kernel<<<blocks, 256, 0, st>>>(part_gb, gb, nc, (int)grid.z);
+    rc = launched("sum_slices");
+    if (rc || !gd) return rc;
+    sum_slices_kernel<<<blocks, 256, 0, st>>>(part_gd, gd, nc, (int)grid.z);
+    return launched("sum_slices");
+}

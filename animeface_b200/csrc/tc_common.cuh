@@ -199,6 +199,34 @@ static inline int make_nhwc_map(CUtensorMap* map, const float* x, int n, int h, 
     return SG2_OK;
 }
 
+// 5-D bf16 map over a "pair planes" tensor [2 planes][n][h][w][c] (hi = bf16(v), lo = bf16(v - hi)): dims (c, w, h, n, plane),
+// box (64 channels = one 128-byte row, bw, bh, bb, 1), SWIZZLE_128B, OOB -> 0.  A box lands in shared memory as rows of 128 B in
+// (b, y, x) order with the 16-byte chunks XOR-swizzled by the row's ABSOLUTE shared-memory address bits [7:9] -- the layout a
+// tcgen05 SWIZZLE_128B descriptor reads, for any row-shifted start address (scripts/exp_umma_shift.cu, profiles/r2a_umma_shift.txt).
+static inline int make_planes_map(CUtensorMap* map, const void* planes, int n, int h, int w, int c, int bw, int bh, int bb, const char* who) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return fail(SG2_ELAUNCH, "%s: cuTensorMapEncodeTiled is not available from the driver", who);
+    if (((uintptr_t)planes & 15) != 0 || (c % 8) != 0) return fail(SG2_EINVAL, "%s: planes must be 16-byte aligned with C %% 8 == 0", who);
+    const cuuint64_t dims[5] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n, 2};
+    const cuuint64_t strides[4] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2, (cuuint64_t)n * h * w * c * 2};
+    const cuuint32_t box[5] = {64u, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb, 1u};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)planes, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SG2_ELAUNCH, "%s: cuTensorMapEncodeTiled failed (%d)", who, (int)r);
+    return SG2_OK;
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+// K-major SWIZZLE_128B descriptor with an explicit stride between 8-row groups (rows of 128 B; the start may sit on any row)
+__device__ __forceinline__ uint64_t kmajor_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
 // Split `total` (128 or 32) pixels into a box of the [n, h, w] grid: as wide as possible first.
 static inline bool pixel_box(int total, int h, int w, int& bw, int& bh, int& bb) {
     auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };

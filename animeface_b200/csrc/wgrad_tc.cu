@@ -46,6 +46,7 @@ struct Params {
     const float* in_scale;    // [n, ci] or null (scales x)
     const float* out_scale;   // [n, co] or null (scales gy)
     float* dw;                // [co, ci, k, k]
+    float* ws;                // partial buffers [split][co, ci, k, k] (deterministic reduction) or null (atomics into dw)
     float coef;
     int n, h, w, ci, co, k;
     int cw, ch, cb, chunks_x, chunks_y, total_chunks;
@@ -265,7 +266,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_tc_kernel(const __grid
                         const int col = col0 + e;
                         const int dxi = col / NT_CI, ci = ci0 + col % NT_CI;
                         const int tap = (KW == 1) ? 0 : dyi * 3 + dxi;
-                        if (ci < p.ci) atomicAdd(p.dw + ((long long)co * p.ci + ci) * kk2 + tap, __uint_as_float(acc[e]) * p.coef);
+                        if (ci < p.ci) {
+                            const long long o = ((long long)co * p.ci + ci) * kk2 + tap;
+                            if (p.ws) p.ws[(long long)blockIdx.y * ((long long)p.co * p.ci * kk2) + o] = __uint_as_float(acc[e]) * p.coef;
+                            else atomicAdd(p.dw + o, __uint_as_float(acc[e]) * p.coef);
+                        }
                     }
                 }
             }
@@ -307,33 +312,46 @@ bool wgrad_tc_supported(int n, int h, int w, int ci, int co, int k) {
     return tc::pixel_box_ragged(wg::CHUNK, h, w, a, b, c);
 }
 
-int conv_wgrad_tc(WgradParams wp, int accumulate, cudaStream_t st) {
-    wg::Params p;
+static int tc_wgrad_plan(const WgradParams& wp, wg::Params& p, int& tiles, int& splits) {
     if (!tc::pixel_box_ragged(wg::CHUNK, wp.h, wp.w, p.cw, p.ch, p.cb)) return fail(SG2_ENOTSUP, "conv_wgrad_tc: unsupported shape");
     if (4 * 64 + 4 * (p.cw + wp.k - 1) * p.ch * p.cb > 32 * wg::XWARPS || (p.cw + wp.k - 1) * p.ch * p.cb > wg::XROWS_MAX)
         return fail(SG2_ENOTSUP, "conv_wgrad_tc: chunk %dx%dx%d does not fit the transform", p.cw, p.ch, p.cb);
-    const int kk2 = wp.k * wp.k;
-    if (!accumulate) {
-        cudaError_t e = cudaMemsetAsync(wp.dw, 0, sizeof(float) * (size_t)wp.co * wp.ci * kk2, st);
-        if (e != cudaSuccess) return fail(SG2_ELAUNCH, "conv_wgrad_tc: memset: %s", cudaGetErrorString(e));
-    }
-    CUtensorMap gmap, xmap;
-    int rc = tc::make_nhwc_map(&gmap, wp.gy, wp.n, wp.h, wp.w, wp.co, p.cw, p.ch, p.cb, "conv_wgrad_tc(gy)");
-    if (rc) return rc;
-    rc = tc::make_nhwc_map(&xmap, wp.x, wp.n, wp.h, wp.w, wp.ci, p.cw + (wp.k - 1), p.ch, p.cb, "conv_wgrad_tc(x)");   // x halo
-    if (rc) return rc;
-    p.in_scale = wp.in_scale; p.out_scale = wp.out_scale; p.dw = wp.dw; p.coef = wp.coef; p.trace = g_trace;
-    p.n = wp.n; p.h = wp.h; p.w = wp.w; p.ci = wp.ci; p.co = wp.co; p.k = wp.k;
-    p.xb = (((p.cw + wp.k - 1) * p.ch * p.cb * 128) + 1023) / 1024 * 1024;
     p.chunks_x = (wp.w + p.cw - 1) / p.cw; p.chunks_y = (wp.h + p.ch - 1) / p.ch;      // ragged: the last chunk of a row overhangs
     p.total_chunks = p.chunks_x * p.chunks_y * ((wp.n + p.cb - 1) / p.cb);
     p.co_tiles = (wp.co + wg::MT - 1) / wg::MT;
     p.ci_tiles = (wp.ci + wg::NT_CI - 1) / wg::NT_CI;
-    const int tiles = p.co_tiles * p.ci_tiles * wp.k;
-    int splits = std::max(1, (2 * num_sms()) / tiles);
+    tiles = p.co_tiles * p.ci_tiles * wp.k;
+    splits = std::max(1, (2 * num_sms()) / tiles);
     splits = std::min(splits, p.total_chunks);
     p.chunks_per_split = (p.total_chunks + splits - 1) / splits;
     splits = (p.total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
+    return SG2_OK;
+}
+
+int wgrad_parts_tc(const WgradParams& wp) {
+    wg::Params p;
+    int tiles, splits;
+    return tc_wgrad_plan(wp, p, tiles, splits) == SG2_OK ? splits : 0;
+}
+
+int conv_wgrad_tc(WgradParams wp, int accumulate, cudaStream_t st) {
+    wg::Params p;
+    int tiles, splits;
+    int rc = tc_wgrad_plan(wp, p, tiles, splits);
+    if (rc) return rc;
+    const int kk2 = wp.k * wp.k;
+    if (!accumulate && !wp.ws) {
+        cudaError_t e = cudaMemsetAsync(wp.dw, 0, sizeof(float) * (size_t)wp.co * wp.ci * kk2, st);
+        if (e != cudaSuccess) return fail(SG2_ELAUNCH, "conv_wgrad_tc: memset: %s", cudaGetErrorString(e));
+    }
+    CUtensorMap gmap, xmap;
+    rc = tc::make_nhwc_map(&gmap, wp.gy, wp.n, wp.h, wp.w, wp.co, p.cw, p.ch, p.cb, "conv_wgrad_tc(gy)");
+    if (rc) return rc;
+    rc = tc::make_nhwc_map(&xmap, wp.x, wp.n, wp.h, wp.w, wp.ci, p.cw + (wp.k - 1), p.ch, p.cb, "conv_wgrad_tc(x)");   // x halo
+    if (rc) return rc;
+    p.in_scale = wp.in_scale; p.out_scale = wp.out_scale; p.dw = wp.dw; p.ws = wp.ws; p.coef = wp.coef; p.trace = g_trace;
+    p.n = wp.n; p.h = wp.h; p.w = wp.w; p.ci = wp.ci; p.co = wp.co; p.k = wp.k;
+    p.xb = (((p.cw + wp.k - 1) * p.ch * p.cb * 128) + 1023) / 1024 * 1024;
     dim3 grid((unsigned)tiles, (unsigned)splits);
     if (wp.k == 3) return wg::launch<3>(gmap, xmap, p, grid, st);
     return wg::launch<1>(gmap, xmap, p, grid, st);

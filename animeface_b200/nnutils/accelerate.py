@@ -114,8 +114,12 @@ class DataLoaderWrapper(DataLoader):
     def __init__(self, dataset, device, **kwargs):
         super().__init__(dataset, **kwargs)
         self._device = device
+        self._epoch = 0
 
     def __iter__(self):
+        if isinstance(self.sampler, torch.utils.data.distributed.DistributedSampler):
+            self.sampler.set_epoch(self._epoch)          # a new shuffle per epoch, the same one on every rank
+        self._epoch += 1
         for batch in super().__iter__():
             yield _to_device(batch, self._device)
 
@@ -127,6 +131,10 @@ class DataLoaderWrapper(DataLoader):
             shuffle = isinstance(dataloader.sampler, torch.utils.data.RandomSampler)
             sampler = torch.utils.data.distributed.DistributedSampler(dataloader.dataset, shuffle=shuffle)
             sampler_kwargs = dict(batch_size=dataloader.batch_size, sampler=sampler, drop_last=dataloader.drop_last)
+        elif world > 1 and not isinstance(dataloader.sampler, torch.utils.data.distributed.DistributedSampler):
+            raise ValueError('MiniAccelerator.prepare: with world_size > 1 a DataLoader needs a plain Random/Sequential sampler '
+                             '(it is re-created with a DistributedSampler) or its own DistributedSampler; a custom sampler / '
+                             'batch_sampler cannot be sharded by rank automatically')
         return cls(dataloader.dataset, device, num_workers=dataloader.num_workers,
                    pin_memory=dataloader.pin_memory, **sampler_kwargs)
 

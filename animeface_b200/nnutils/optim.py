@@ -77,6 +77,50 @@ class FlatAdam(torch.optim.Optimizer):
     def flat_grads(self):
         return self._G
 
+    # ---- checkpointing: torch.optim.Adam's layout (state[i] = {step, exp_avg, exp_avg_sq}), so FlatAdam and
+    # torch.optim.Adam checkpoints are interchangeable and a resume restores the moments and the bias correction.
+    def state_dict(self):
+        steps = self._steps.tolist()
+        state = {}
+        for i, (o, n, p) in enumerate(zip(self._offs, self._sizes, self._ps)):
+            if steps[i] == 0:
+                continue                                   # torch.optim.Adam has no entry for a never-stepped tensor
+            state[i] = dict(step=torch.tensor(float(steps[i])),
+                            exp_avg=self._M[o:o + n].view(p.shape).clone(),
+                            exp_avg_sq=self._V[o:o + n].view(p.shape).clone())
+        group = {k: v for k, v in self.param_groups[0].items() if k != 'params'}
+        group['params'] = list(range(len(self._ps)))
+        return dict(state=state, param_groups=[group])
+
+    @torch.no_grad()
+    def load_state_dict(self, state_dict):
+        groups = state_dict['param_groups']
+        if len(groups) != 1 or len(groups[0]['params']) != len(self._ps):
+            raise ValueError('FlatAdam.load_state_dict: the checkpoint has a different parameter list')
+        for k, v in groups[0].items():
+            if k != 'params' and k in self.param_groups[0]:
+                self.param_groups[0][k] = v
+        self._M.zero_(); self._V.zero_()
+        steps = [0] * len(self._ps)
+        for key, st in state_dict['state'].items():
+            i = int(key)
+            o, n, p = self._offs[i], self._sizes[i], self._ps[i]
+            if tuple(st['exp_avg'].shape) != tuple(p.shape):
+                raise ValueError(f'FlatAdam.load_state_dict: state {i} has shape {tuple(st["exp_avg"].shape)}, parameter {tuple(p.shape)}')
+            self._M[o:o + n].copy_(st['exp_avg'].reshape(-1))
+            self._V[o:o + n].copy_(st['exp_avg_sq'].reshape(-1))
+            steps[i] = int(float(st['step']))
+        self._steps.copy_(torch.tensor(steps, dtype=torch.int64))
+
+    def _check_views(self):
+        """The parameters must still be the views of the flat buffer made in __init__: ``model.to(...)``, ``.half()`` or a
+        ``p.data = ...`` afterwards would leave the optimizer updating a buffer nobody reads."""
+        base = self._P.data_ptr()
+        for p, o in zip(self._ps, self._offs):
+            if p.data_ptr() != base + 4 * o:
+                raise RuntimeError('FlatAdam: a parameter no longer aliases the flat buffer (model moved / re-typed / .data '
+                                   're-assigned after the optimizer was built); build the optimizer last')
+
     def zero_grad(self, set_to_none: bool = True):
         for p in self._ps:
             p.grad = None
@@ -89,6 +133,7 @@ class FlatAdam(torch.optim.Optimizer):
         present = [i for i, p in enumerate(self._ps) if p.grad is not None]
         if not present:
             return
+        self._check_views()
         torch._foreach_copy_([self._gviews[i] for i in present], [self._ps[i].grad for i in present])
         scale = 1.0
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:

@@ -132,10 +132,89 @@ def _wgrad_raw(x, gy, k, coef, in_scale=None, out_scale=None, impl=None):
     dw = torch.empty((co, ci, k, k), dtype=torch.float32, device=x.device)
     f32 = lambda t: None if t is None else t.detach().to(torch.float32).contiguous()
     in_scale, out_scale = f32(in_scale), f32(out_scale)
+    ws = _workspace(lib.sg2_conv2d_wgrad_workspace(n, h, wd, ci, co, k, impl), x.device, 'sg2_conv2d_wgrad_workspace')
     with _timed('wgrad', 2.0 * n * h * wd * ci * co * k * k):
         _lib.check(lib.sg2_conv2d_wgrad(x.data_ptr(), gy.data_ptr(), dw.data_ptr(), n, h, wd, ci, co, k, float(coef),
-                                        _lib.ptr(in_scale), _lib.ptr(out_scale), 0, impl, _lib.stream_ptr(x)),
+                                        _lib.ptr(in_scale), _lib.ptr(out_scale), 0, impl, ws.data_ptr(), _lib.stream_ptr(x)),
                    'sg2_conv2d_wgrad')
+    return dw
+
+
+# ----------------------------------------------------------------------------------------------
+# bf16 pair planes (csrc/planes.cu): the first-order backward fast path.  A gradient tensor / activation is written ONCE
+# as hi = bf16(v), lo = bf16(v - hi) ([2][n,h,w,c], 4 bytes per element) by the elementwise pass that touches it anyway;
+# the tcgen05 data-gradient and weight-gradient kernels then take their operands by TMA straight into swizzled tiles.
+
+planes_enabled = True           # tests / A-B measurements flip this to compare with the fp32-operand kernels
+
+
+def _workspace(nbytes: int, device, what: str) -> torch.Tensor:
+    """Scratch for the deterministic two-pass reductions (every split stores its partial, a second kernel adds them in a
+    fixed order).  Allocated per call from torch's caching allocator, so it is stream-ordered and capture-safe."""
+    if nbytes < 0:
+        raise RuntimeError(f'{what}: unsupported shape')
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _planes_ok(n, h, wd, cin, cout, k, wgrad: bool) -> bool:
+    return planes_enabled and bool(_lib.load().sg2_conv2d_planes_supported(n, h, wd, cin, cout, k, 1 if wgrad else 0))
+
+
+def _split_planes(x, scale=None):
+    """planes[2][n,h,w,c] = split(x * scale[b,c]); x channels_last fp32."""
+    lib = _lib.load()
+    n, c, h, wd = x.shape
+    x = _cl(x)
+    planes = torch.empty((2, n, h, wd, c), dtype=torch.bfloat16, device=x.device)
+    sc = None if scale is None else scale.detach().to(torch.float32).contiguous()
+    _lib.check(lib.sg2_split_planes(x.data_ptr(), _lib.ptr(sc), planes.data_ptr(), n, h * wd, c, _lib.stream_ptr(x)), 'sg2_split_planes')
+    return planes
+
+
+def _bwd_prep_planes(gy, y, slope, noise=None, bias=None, d=None):
+    """One pass over (gy, y): gu = gy * lrelu'(y) (slope None: gu = gy, y is not read); returns (planes of gu * d, gb [co],
+    gd [n,co] or None).  The per-(sample, channel) sums are reduced in a fixed order (deterministic)."""
+    lib = _lib.load()
+    n, co, h, wd = gy.shape
+    gy = _cl(gy)
+    yc = None if (slope is None and d is None) else _cl(y)      # y gives the leaky-ReLU sign and, for gd, the accumulator
+    planes = torch.empty((2, n, h, wd, co), dtype=torch.bfloat16, device=gy.device)
+    gb = torch.empty((n, co), dtype=torch.float32, device=gy.device)
+    gd = torch.empty((n, co), dtype=torch.float32, device=gy.device) if d is not None else None
+    ws = _workspace(lib.sg2_bwd_prep_planes_workspace(n, h * wd, co), gy.device, 'sg2_bwd_prep_planes_workspace')
+    f32 = lambda t: None if t is None else t.detach().to(torch.float32).contiguous()
+    noise, bias, d = f32(noise), (None if bias is None else f32(bias).reshape(-1)), f32(d)
+    _lib.check(lib.sg2_bwd_prep_planes(gy.data_ptr(), _lib.ptr(yc), _lib.ptr(noise), _lib.ptr(bias), _lib.ptr(d), planes.data_ptr(),
+                                       gb.data_ptr(), _lib.ptr(gd), ws.data_ptr(), n, h * wd, co,
+                                       float(slope if slope is not None else 1.0), _lib.stream_ptr(gy)), 'sg2_bwd_prep_planes')
+    return planes, gb.sum(0), gd
+
+
+def _conv_planes(xp, w, coef, transpose):
+    """y = conv(x, w*coef) (transpose: the data gradient) with x given as pair planes [2][n,h,w,cin]; bf16x3 halo kernel."""
+    lib = _lib.load()
+    co, ci, k, _ = w.shape
+    cin, cout = (co, ci) if transpose else (ci, co)
+    _, n, h, wd, cx = xp.shape
+    assert cx == cin
+    packed = _pack(w, coef, transpose, IMPL_HALO)
+    y = torch.empty_strided((n, cout, h, wd), (h * wd * cout, 1, wd * cout, cout), dtype=torch.float32, device=xp.device)
+    with _timed('dgrad' if transpose else 'fwd', 2.0 * n * h * wd * cin * cout * k * k):
+        _lib.check(lib.sg2_conv2d_fwd_planes(xp.data_ptr(), packed.data_ptr(), y.data_ptr(), _lib.strides4(y), n, h, wd, cin, cout, k,
+                                             None, None, 1, 0.0, 1.0, _lib.stream_ptr(xp)), 'sg2_conv2d_fwd_planes')
+    return y
+
+
+def _wgrad_planes(xp, gyp, k, coef):
+    """dw[co,ci,k,k] = coef * sum gy (x) x, both operands as pair planes; deterministic."""
+    lib = _lib.load()
+    _, n, h, wd, ci = xp.shape
+    co = gyp.shape[4]
+    dw = torch.empty((co, ci, k, k), dtype=torch.float32, device=xp.device)
+    ws = _workspace(lib.sg2_conv2d_wgrad_planes_workspace(n, h, wd, ci, co, k), xp.device, 'sg2_conv2d_wgrad_planes_workspace')
+    with _timed('wgrad', 2.0 * n * h * wd * ci * co * k * k):
+        _lib.check(lib.sg2_conv2d_wgrad_planes(xp.data_ptr(), gyp.data_ptr(), dw.data_ptr(), ws.data_ptr(), n, h, wd, ci, co, k,
+                                               float(coef), 0, _lib.stream_ptr(xp)), 'sg2_conv2d_wgrad_planes')
     return dw
 
 
@@ -231,20 +310,32 @@ class ConvBiasActFn(torch.autograd.Function):
             if ctx.needs_input_grad[2]:
                 gb = gu.sum((0, 2, 3))
         else:
+            n, ci, h, wd = x.shape
+            k = w.shape[2]
+            need_gx, need_gw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+            use_planes = ((need_gx or need_gw) and (not need_gx or _planes_ok(n, h, wd, co, ci, k, False))
+                          and (not need_gw or _planes_ok(n, h, wd, ci, co, k, True)))
+            if use_planes:
+                # first-order fast path: ONE pass over (gy, y) writes gu = gy * lrelu'(y) as bf16 pair planes (+ the bias
+                # gradient); data and weight gradient take them by TMA, no fp32 -> bf16 transform inside the kernels
+                gup, gb, _ = _bwd_prep_planes(gy, y, ctx.slope)
+                gx = _conv_planes(gup, w, ctx.coef, True) if need_gx else None
+                gw = _wgrad_planes(_split_planes(x), gup, k, ctx.coef) if need_gw else None
+                return gx, gw, (gb if ctx.needs_input_grad[2] else None), None, None
             # first-order backward: leaky-ReLU mask and the bias-gradient reduction in ONE pass over (gy, y)
             lib = _lib.load()
-            n, _, h, wd = gy.shape
             gyc = _cl(gy)
             part = torch.empty((n, co), dtype=torch.float32, device=gy.device)
+            ws = _workspace(lib.sg2_reduce_hw_workspace(n, h * wd, co), gy.device, 'sg2_reduce_hw_workspace')
             if ctx.slope is not None:
                 gu = _empty_cl(n, co, h, wd, gy)
                 _lib.check(lib.sg2_modconv_bwd_prep(gyc.data_ptr(), _cl(y).data_ptr(), None, None, None, gu.data_ptr(),
                                                     part.data_ptr(), None, n, h * wd, co, float(ctx.slope),
-                                                    _lib.stream_ptr(gy)), 'sg2_modconv_bwd_prep')
+                                                    ws.data_ptr(), _lib.stream_ptr(gy)), 'sg2_modconv_bwd_prep')
             else:
                 gu = gyc
-                _lib.check(lib.sg2_reduce_hw(gyc.data_ptr(), None, part.data_ptr(), n, h * wd, co, _lib.stream_ptr(gy)),
-                           'sg2_reduce_hw')
+                _lib.check(lib.sg2_reduce_hw(gyc.data_ptr(), None, part.data_ptr(), n, h * wd, co, ws.data_ptr(),
+                                             _lib.stream_ptr(gy)), 'sg2_reduce_hw')
             gb = part.sum(0)
         gx = gw = None
         if ctx.needs_input_grad[0]:
@@ -287,16 +378,22 @@ class ModConvFn(torch.autograd.Function):
         co, k = w.shape[0], w.shape[2]
         st = _lib.stream_ptr(x)
         x = _cl(x)
-        if co % 4 == 0:
+        need_gw = ctx.needs_input_grad[1]
+        use_planes = (co % 4 == 0 and _planes_ok(n, h, wd, co, ci, k, False) and (not need_gw or _planes_ok(n, h, wd, ci, co, k, True)))
+        g_acc_p = None
+        if use_planes:
+            g_acc_p, gb, gd = _bwd_prep_planes(gy, y, ctx.slope, noise=noise, bias=b, d=d)
+        elif co % 4 == 0:
             gy, yc = _cl(gy), _cl(y)
             g_acc = _empty_cl(n, co, h, wd, x)
             gb_part = torch.empty((n, co), dtype=torch.float32, device=x.device)
             gd = torch.empty((n, co), dtype=torch.float32, device=x.device) if d is not None else None
             bflat = None if b is None else b.detach().reshape(-1).contiguous()
+            ws = _workspace(lib.sg2_reduce_hw_workspace(n, h * wd, co), x.device, 'sg2_reduce_hw_workspace')
             _lib.check(lib.sg2_modconv_bwd_prep(
                 gy.data_ptr(), yc.data_ptr(), _lib.ptr(noise), _lib.ptr(bflat), _lib.ptr(d), g_acc.data_ptr(),
                 gb_part.data_ptr(), _lib.ptr(gd), n, h * wd, co,
-                float(ctx.slope if ctx.slope is not None else 1.0), st), 'sg2_modconv_bwd_prep')
+                float(ctx.slope if ctx.slope is not None else 1.0), ws.data_ptr(), st), 'sg2_modconv_bwd_prep')
             gb = gb_part.sum(0)
         else:
             # few output channels (ToRGB, Co=3): the tensors are tiny, keep this prologue in torch.
@@ -306,18 +403,22 @@ class ModConvFn(torch.autograd.Function):
             gd = None
         gx = gw = gs = None
         # data gradient w.r.t. the modulated input, then gs = sum_hw g_xs * x and gx = g_xs * s in one pass
-        g_xs = _conv_raw(g_acc, w, ctx.coef, True)
+        g_xs = _conv_planes(g_acc_p, w, ctx.coef, True) if use_planes else _conv_raw(g_acc, w, ctx.coef, True)
         if ci % 4 == 0:
             gs = torch.empty((n, ci), dtype=torch.float32, device=x.device)
             gx = _empty_cl(n, ci, h, wd, x) if ctx.needs_input_grad[0] else None
             sc = s.detach().contiguous()
+            ws = _workspace(lib.sg2_reduce_hw_workspace(n, h * wd, ci), x.device, 'sg2_reduce_hw_workspace')
             _lib.check(lib.sg2_scale_reduce_hw(g_xs.data_ptr(), x.data_ptr(), sc.data_ptr(), _lib.ptr(gx),
-                                               gs.data_ptr(), n, h * wd, ci, st), 'sg2_scale_reduce_hw')
+                                               gs.data_ptr(), n, h * wd, ci, ws.data_ptr(), st), 'sg2_scale_reduce_hw')
         else:
             gs = (g_xs * x).sum((2, 3))
             gx = g_xs * s[:, :, None, None]
-        if ctx.needs_input_grad[1]:
-            gw = _wgrad_raw(x, g_acc, k, ctx.coef, in_scale=s)
+        if need_gw:
+            if use_planes:
+                gw = _wgrad_planes(_split_planes(x, s), g_acc_p, k, ctx.coef)
+            else:
+                gw = _wgrad_raw(x, g_acc, k, ctx.coef, in_scale=s)
         if b is not None:
             gb = gb.reshape(b.shape)
         return gx, gw, gs, gd, (gb if b is not None else None), None, None, None, None

@@ -22,12 +22,13 @@ import math
 from dataclasses import dataclass
 
 import torch
+import torch.distributed as dist
 
 from . import rng
 from .ops.conv2d import any_order_modconv
 from .diffaugment import DiffAugment
 from .model import Discriminator, Generator, independent_batches, init_weight_N01, supplied_noise  # noqa: F401
-from .nnutils import FlatAdam, update_ema
+from .nnutils import FlatAdam, init_distributed, update_ema
 from .nnutils.loss import NonSaturatingLoss, calc_grad, r1_regularizer
 
 
@@ -73,7 +74,10 @@ class TrainConfig:
 
 
 def build_models(cfg: TrainConfig, device):
-    """Models + init exactly as utils.py:186-205."""
+    """Models + init exactly as utils.py:186-205.  Under torchrun (one process per GPU) the process group is initialised
+    here, rank 0's freshly initialised weights are broadcast so the replicas start identical whatever each rank's seed is,
+    and every rank then moves its generators to a rank-distinct stream (latents, noise and augmentation draws must differ
+    between ranks -- identical draws would make the global batch `world` copies of one batch)."""
     mk_g = lambda: Generator(cfg.image_size, cfg.image_channels, cfg.style_dim, cfg.channels, cfg.max_channels,
                              cfg.block_num_conv, cfg.map_num_layers, True, cfg.map_lr)
     G, G_ema = mk_g(), mk_g()
@@ -82,7 +86,16 @@ def build_models(cfg: TrainConfig, device):
     G_ema.eval()
     G_ema.load_state_dict(G.state_dict())       # == update_ema(G, G_ema, decay=0) on finite memory (utils.py:199-200)
     D.apply(init_weight_N01)
-    return G.to(device), G_ema.to(device), D.to(device)
+    G, G_ema, D = G.to(device), G_ema.to(device), D.to(device)
+    init_distributed()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        with torch.no_grad():
+            for m in (G, G_ema, D):
+                for t in list(m.parameters()) + list(m.buffers()):
+                    dist.broadcast(t.data, src=0)
+        seed = torch.initial_seed() + 7919 * (dist.get_rank() + 1)
+        torch.manual_seed(seed)                     # seeds the CPU and every CUDA generator of this process
+    return G, G_ema, D
 
 
 def build_optimizers(cfg: TrainConfig, G, G_ema, D):
@@ -192,13 +205,16 @@ class GraphedTrainer:
     path-length running mean live on the device; under torchrun the NCCL all-reduce of the flat gradient buffer is
     captured with the rest.  Policy: the first step of each kind runs eagerly (it also warms kernels up), the second
     one is captured and replayed, later ones are replays.  ``prime()`` does that up front for every kind of the
-    schedule."""
+    schedule.  A batch of another size (ragged last batch) runs the eager step; a change of lr / betas / eps drops the
+    captured graphs (they hold those values as kernel scalars)."""
 
-    def __init__(self, trainer: Trainer):
+    def __init__(self, trainer: Trainer, eager_first: bool = True):
         self.t = trainer
+        self.eager_first = eager_first      # False: capture a kind at its first occurrence (caller has warmed the kernels up)
         self.static_real = None
         self.graphs = {}          # kind (is_r1, is_pl) -> (CUDAGraph, outputs)
         self.seen = set()
+        self._hparams = None
 
     def kinds(self):
         """Step kinds of the lazy-regularisation schedule, most frequent first."""
@@ -210,24 +226,36 @@ class GraphedTrainer:
         return out
 
     def prime(self, real):
-        """Eager + capture for every kind now (2 extra optimizer steps per kind, out of schedule)."""
+        """Eager + capture for every kind now (2 extra optimizer steps per kind); the schedule position is kept."""
+        done = self.t.batches_done
         for kind in self.kinds():
             self.step(real, *kind)
             self.step(real, *kind)
+        self.t.batches_done = done
+
+    def _current_hparams(self):
+        # lr / betas / eps are kernel scalars baked into a captured graph: a change must re-capture
+        return tuple((g['lr'], tuple(g['betas']), g['eps']) for o in (self.t.opt_g, self.t.opt_d) for g in o.param_groups)
 
     def step(self, real, force_r1=None, force_pl=None):
         t = self.t
         kind = (t.is_r1_step() if force_r1 is None else bool(force_r1),
                 t.is_pl_step() if force_pl is None else bool(force_pl))
+        hp = self._current_hparams()
+        if self._hparams != hp:
+            self.graphs.clear()
+            self._hparams = hp
         if self.static_real is None:
             self.static_real = real.clone()
+        if real.shape != self.static_real.shape:
+            return t.step(real, *kind)          # ragged last batch of a loader: the eager step takes any batch size
         if kind in self.graphs:
             self.static_real.copy_(real)
             g, out = self.graphs[kind]
             g.replay()
             t.batches_done += 1
             return out
-        if kind not in self.seen:
+        if self.eager_first and kind not in self.seen:
             self.seen.add(kind)
             return t.step(real, *kind)
         self.static_real.copy_(real)
@@ -244,10 +272,18 @@ class GraphedTrainer:
 
 
 def train(max_iter, dataset, cfg: TrainConfig, device, log_every=100, log=print):
-    """Minimal counterpart of the reference ``train()`` (utils.py:35-138): iterate a loader of real batches."""
+    """Minimal counterpart of the reference ``train()`` (utils.py:35-138): iterate a loader of real batches.
+    Under torchrun every rank runs this function: replicas are synchronised in ``build_models``, gradients in
+    ``FlatAdam.step``; a ``DataLoader`` is sharded by rank (``MiniAccelerator.prepare``), any other iterable is taken
+    as already rank-local."""
     G, G_ema, D = build_models(cfg, device)
     opt_g, opt_d = build_optimizers(cfg, G, G_ema, D)
     trainer = Trainer(cfg, G, G_ema, D, opt_g, opt_d)
+    if isinstance(dataset, torch.utils.data.DataLoader):
+        from .nnutils import MiniAccelerator
+        dataset = MiniAccelerator(amp=False, device=device).prepare(dataset)
+    rank0 = not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
+    log = log if rank0 else (lambda *a, **k: None)
     while trainer.batches_done < max_iter:
         for real in dataset:
             d_loss, g_loss, _ = trainer.step(real.to(device, non_blocking=True))

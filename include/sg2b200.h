@@ -166,11 +166,15 @@ int sg2_conv2d_fwd(const float* x, const void* packed_w, float* y, const int64_t
 /* weight gradient: dw[co][ci][k][k] (reference layout) = coef * sum_{n,h,w} gy (x) x.
  * x [n,h,w,ci], gy [n,h,w,co] NHWC dense.  in_scale [n,ci] / out_scale [n,co]
  * optional: x is taken as x*in_scale and gy as gy*out_scale (modulated layers).
- * accumulate=0 overwrites dw, 1 adds into it.                                 */
+ * accumulate=0 overwrites dw, 1 adds into it.
+ * workspace: sg2_conv2d_wgrad_workspace(...) bytes, or NULL.  With a workspace every pixel split stores its partial dw and
+ * a second kernel adds the splits in a fixed order: run-to-run identical results (what CUDA-graph replay == eager needs).
+ * NULL keeps the one-pass fp32-atomic reduction (order, and so the last bits, vary from run to run).                   */
+int64_t sg2_conv2d_wgrad_workspace(int n, int h, int w, int ci, int co, int k, int impl);
 int sg2_conv2d_wgrad(const float* x, const float* gy, float* dw,
                      int n, int h, int w, int ci, int co, int k, float coef,
                      const float* in_scale, const float* out_scale,
-                     int accumulate, int impl, sg2_stream_t stream);
+                     int accumulate, int impl, void* workspace, sg2_stream_t stream);
 
 /* per-(sample,channel) reductions used by the modulated-conv backward ------- *
  * replaces: the autograd graph of ModulatedConv2d.forward
@@ -178,17 +182,52 @@ int sg2_conv2d_wgrad(const float* x, const float* gy, float* dw,
  * a, bm, a_out: [n,hw,c] NHWC dense, c % 4 == 0.
  *   out[b,c]   = sum_hw a * (bm ? bm : 1)         (d s[b,i] = sum_hw x * g_xs)
  *   a_out      = a * scale[b,c]   when a_out != NULL  (g_x = g_xs * s, same pass)  */
+/* workspace (all three calls below): sg2_reduce_hw_workspace(n, hw, c) bytes for a deterministic two-pass reduction over the
+ * hw slices, or NULL for one pass with fp32 atomics.                                                                      */
+int64_t sg2_reduce_hw_workspace(int n, int hw, int c);
 int sg2_reduce_hw(const float* a, const float* bm, float* out,
-                  int n, int hw, int c, sg2_stream_t stream);
+                  int n, int hw, int c, void* workspace, sg2_stream_t stream);
 int sg2_scale_reduce_hw(const float* a, const float* bm, const float* scale,
-                        float* a_out, float* out, int n, int hw, int c, sg2_stream_t stream);
+                        float* a_out, float* out, int n, int hw, int c, void* workspace, sg2_stream_t stream);
 /* backward prologue of y = lrelu_alpha(d * acc + bias + noise) in ONE pass over (gy, y):
  *   gu = gy * (y > 0 ? 1 : alpha);  g_acc = gu * d;  gb_part[b,o] = sum_hw gu;
  *   gd[b,o] = sum_hw gu * acc,  acc recovered from y as (u - bias - noise)/d.
  * alpha = 1 means "no activation".  d, gd, bias, noise may be NULL.           */
 int sg2_modconv_bwd_prep(const float* gy, const float* y, const float* noise, const float* bias,
                          const float* d, float* g_acc, float* gb_part, float* gd,
-                         int n, int hw, int c, float alpha, sg2_stream_t stream);
+                         int n, int hw, int c, float alpha, void* workspace, sg2_stream_t stream);
+
+/* bf16 pair planes: the first-order backward fast path ----------------------- *
+ * replaces: the same ATen convolution_backward calls as sg2_conv2d_fwd(transposed pack) / sg2_conv2d_wgrad above
+ *           (implementations/StyleGAN2/model.py:129, 44-53), for operands that an elementwise pass has already
+ *           written as "pair planes": hi = bf16(v), lo = bf16(v - hi), stored back to back as [2][n][hw][c] bf16
+ *           (4 bytes per element, like the fp32 tensor they stand for).  The tcgen05 kernels then take their
+ *           operands by TMA straight into swizzled tiles -- no in-kernel fp32 -> bf16 conversion -- and the k*k taps
+ *           are descriptor offsets into ONE tile.  bf16x3 arithmetic (~5e-6 relative), as impl 4.
+ * sg2_split_planes:    planes = split(x * scale[b,c])   (scale may be NULL)                        c % 4 == 0
+ * sg2_bwd_prep_planes: sg2_modconv_bwd_prep with g_acc written as planes and DETERMINISTIC per-(sample, channel) sums:
+ *                      gb[n,c] = sum_hw gu, gd[n,c] = sum_hw gu * acc (NULL = skip); y NULL = no activation (gu = gy);
+ *                      workspace: sg2_bwd_prep_planes_workspace(n, hw, c) bytes.
+ * sg2_conv2d_fwd_planes: y = gain * act(out_scale * conv(x, w) + bias) with x given as planes [2][n,h,w,ci]
+ *                      (ci % 64 == 0); packed_w from sg2_conv2d_pack_weight(impl = 4) -- with transpose = 1 this is the
+ *                      data gradient.  sg2_conv2d_planes_supported(.., wgrad = 0) tells whether the shape is taken.
+ * sg2_conv2d_wgrad_planes: dw[co][ci][k][k] (+)= coef * sum gy (x) x with both operands as planes (ci, co % 64 == 0,
+ *                      image width >= 8); run-to-run deterministic (two-pass split-K through `workspace`,
+ *                      sg2_conv2d_wgrad_planes_workspace bytes).                                                    */
+int sg2_split_planes(const float* x, const float* scale, void* planes, int n, int hw, int c, sg2_stream_t stream);
+int64_t sg2_bwd_prep_planes_workspace(int n, int hw, int c);
+int sg2_bwd_prep_planes(const float* gy, const float* y, const float* noise, const float* bias, const float* d,
+                        void* planes, float* gb, float* gd, void* workspace,
+                        int n, int hw, int c, float alpha, sg2_stream_t stream);
+int sg2_conv2d_planes_supported(int n, int h, int w, int ci, int co, int k, int wgrad);
+int sg2_conv2d_fwd_planes(const void* x_planes, const void* packed_w, float* y, const int64_t y_strides[4],
+                          int n, int h, int w, int ci, int co, int k,
+                          const float* out_scale, const float* bias, int act, float alpha, float gain,
+                          sg2_stream_t stream);
+int64_t sg2_conv2d_wgrad_planes_workspace(int n, int h, int w, int ci, int co, int k);
+int sg2_conv2d_wgrad_planes(const void* x_planes, const void* gy_planes, float* dw, void* workspace,
+                            int n, int h, int w, int ci, int co, int k, float coef, int accumulate,
+                            sg2_stream_t stream);
 
 /* optimizer ---------------------------------------------------------------- *
  * replaces: torch.optim.Adam.step (implementations/StyleGAN2/utils.py:220-221,

@@ -140,11 +140,11 @@ def gen_modules():
             out[f'mod.{name}.{k_}'] = A(t)
         out[f'mod.{name}.demod'] = np.array(demod)
     # DBlock forward + gradients + double backward (R1 pattern)
+    # every parameter is drawn from the seeded generator `g` (init_weight_N01's N(0,1) weights; non-zero biases so their
+    # gradients are exercised): the file regenerates bit for bit
     blk = ref_model.DBlock(8, 16, 2)
-    blk.apply(ref_model.init_weight_N01)
     for p in blk.parameters():
-        if p.ndim == 1:
-            p.data.copy_(rn(*p.shape) * 0.3)
+        p.data.copy_(rn(*p.shape) * (0.3 if p.ndim == 1 else 1.0))
     x = rn(4, 8, 8, 8).requires_grad_(True)
     y = blk(x)
     gy = rn(*y.shape)
@@ -424,8 +424,9 @@ def gen_sg3d():
 
 
 if __name__ == '__main__':
-    if len(sys.argv) > 1 and sys.argv[1] in ('pl', 'sg3d'):       # only one of the files added later (the others are unchanged)
-        dict(pl=gen_pl, sg3d=gen_sg3d)[sys.argv[1]]()
+    if len(sys.argv) > 1:                                         # regenerate only the named files
+        for name in sys.argv[1:]:
+            dict(ops=gen_ops, modules=gen_modules, model=gen_model, pl=gen_pl, sg3d=gen_sg3d)[name]()
         sys.exit(0)
     gen_ops()
     gen_modules()
