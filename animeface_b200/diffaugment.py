@@ -1,19 +1,90 @@
 """DiffAugment ('color', 'translation', 'cutout') with the reference's signature and draw order.
 
 Reference: thirdparty/diffaugment/DiffAugment.py:10-77.  Same arithmetic and the same sequence of random
-draws (3 x rand(B,1,1,1) for colour, 2 x randint for translation / cutout); the translation is a pair of
-1-D gathers on a zero-padded copy instead of the reference's NHWC permute + 3-D advanced indexing
-(~10 passes over the batch), and stays differentiable w.r.t. x.
+draws (3 x rand(B,1,1,1) for colour, 2 x randint for translation / cutout).  On the training path (CUDA fp32 NCHW
+images, policy a subset of 'color,translation,cutout' in that order) the whole policy is ONE fused kernel pass forward
+and one backward (csrc/diffaug.cu) instead of the reference's ~10 elementwise / reduction / gather passes; the op is
+affine in x, its backward kernel is the transpose and the pair is closed under differentiation.  Any other policy
+order / layout takes the per-op functions below (gather-based translation), which stay differentiable w.r.t. x.
 """
 from __future__ import annotations
 
 import torch
 import torch.nn.functional as F
 
-from . import rng
+from . import _lib, rng
+
+_CANON = ('color', 'translation', 'cutout')
+
+
+class _Draws:
+    """The random draws of one DiffAugment call, in the reference's order (DiffAugment.py:24,30,36,42-43,58-59)."""
+
+    def __init__(self, x, parts, cutout_ratio=0.5, translation_ratio=0.125):
+        B, C, H, W = x.shape
+        dev = x.device
+        self.rb = self.rs = self.rc = self.ty = self.tx = self.cy = self.cx = None
+        self.cut_h = self.cut_w = 0
+        if 'color' in parts:
+            self.rb = rng.rand(B, 1, 1, 1, device=dev).reshape(B).contiguous()
+            self.rs = rng.rand(B, 1, 1, 1, device=dev).reshape(B).contiguous()
+            self.rc = rng.rand(B, 1, 1, 1, device=dev).reshape(B).contiguous()
+        if 'translation' in parts:
+            sh, sw = int(H * translation_ratio + 0.5), int(W * translation_ratio + 0.5)
+            self.ty = rng.randint(-sh, sh + 1, (B, 1, 1), device=dev).reshape(B).to(torch.int64).contiguous()
+            self.tx = rng.randint(-sw, sw + 1, (B, 1, 1), device=dev).reshape(B).to(torch.int64).contiguous()
+        if 'cutout' in parts:
+            self.cut_h, self.cut_w = int(H * cutout_ratio + 0.5), int(W * cutout_ratio + 0.5)
+            self.cy = rng.randint(0, H + (1 - self.cut_h % 2), (B, 1, 1), device=dev).reshape(B).to(torch.int64).contiguous()
+            self.cx = rng.randint(0, W + (1 - self.cut_w % 2), (B, 1, 1), device=dev).reshape(B).to(torch.int64).contiguous()
+
+
+def _launch(x, d, backward, linear_only):
+    lib = _lib.load()
+    B, C, H, W = x.shape
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    ws = torch.empty(max(int(lib.sg2_diffaugment_workspace(B, H, W)), 16), dtype=torch.uint8, device=x.device)
+    _lib.check(lib.sg2_diffaugment(x.data_ptr(), y.data_ptr(), _lib.ptr(d.rb), _lib.ptr(d.rs), _lib.ptr(d.rc), _lib.ptr(d.ty), _lib.ptr(d.tx),
+                                   _lib.ptr(d.cy), _lib.ptr(d.cx), d.cut_h, d.cut_w, B, C, H, W, 1 if backward else 0,
+                                   1 if linear_only else 0, ws.data_ptr(), _lib.stream_ptr(x)), 'sg2_diffaugment')
+    return y
+
+
+class _AugFn(torch.autograd.Function):
+    """y = A x + c (the fused policy); linear_only drops c (that is the derivative of the backward op below)."""
+
+    @staticmethod
+    def forward(ctx, x, d, linear_only):
+        ctx.d = d
+        return _launch(x, d, False, linear_only)
+
+    @staticmethod
+    def backward(ctx, gy):
+        return _AugTFn.apply(gy, ctx.d), None, None
+
+
+class _AugTFn(torch.autograd.Function):
+    """gx = A^T gy"""
+
+    @staticmethod
+    def forward(ctx, gy, d):
+        ctx.d = d
+        return _launch(gy, d, True, False)
+
+    @staticmethod
+    def backward(ctx, ggx):
+        return _AugFn.apply(ggx, ctx.d, True), None
+
+
+def _fused_ok(x, parts):
+    return (x.is_cuda and x.dtype == torch.float32 and x.ndim == 4 and x.shape[1] <= 8 and len(parts) > 0
+            and all(p in _CANON for p in parts) and [p for p in _CANON if p in parts] == parts)
 
 
 def DiffAugment(x, policy='', channels_first=True):
+    if policy and channels_first and _fused_ok(x, policy.split(',')):
+        return _AugFn.apply(x, _Draws(x, policy.split(',')), False)
     if policy:
         if not channels_first:
             x = x.permute(0, 3, 1, 2)

@@ -24,6 +24,7 @@ import torch.nn.functional as F
 from . import rng
 from .ops import conv2d as C
 from .ops.bias_act import bias_act
+from .ops.linear import linear_bias_act, pixel_norm
 from .ops.mbstd import minibatch_stddev
 from .ops.resample import avgpool2, upsample2x_bilinear, upsample2x_blur
 
@@ -43,7 +44,7 @@ class ELR(nn.Module):
 
     def forward(self, x):
         if isinstance(self.layer, nn.Linear):
-            return F.linear(x, self.layer.weight * self.coef, self.layer.bias)
+            return linear_bias_act(x, self.layer.weight, self.layer.bias, self.coef)
         pad = self.layer.padding[0]
         assert self.layer.stride == (1, 1) and 2 * pad + 1 == self.layer.kernel_size[0], 'stride-1 same conv only'
         return C.conv2d_bias_act(x, self.layer.weight, self.layer.bias, self.coef, None)
@@ -94,8 +95,10 @@ class MapLinear(nn.Module):
         self.linear = Linear('elr', *args, **kwargs)
         self.lr = lr
 
-    def forward(self, x):
-        return self.linear(x) * self.lr
+    def forward(self, x, slope=None):
+        # (layer(x * coef)) * lr [-> LeakyReLU]: one launch (ops/linear.py)
+        lin = self.linear
+        return linear_bias_act(x, lin.layer.weight, lin.layer.bias, lin.coef, self.lr, slope)
 
 
 class supplied_noise(rng.replay):
@@ -249,7 +252,7 @@ class ToImage(nn.Module):
 
 class PixelNorm(nn.Module):
     def forward(self, x):
-        return x / (x.pow(2).mean(dim=1, keepdim=True).sqrt() + 1e-4)
+        return pixel_norm(x, 1e-4)
 
 
 class Mapping(nn.Module):
@@ -264,7 +267,17 @@ class Mapping(nn.Module):
     def forward(self, x):
         if self.normalize is not None:
             x = self.normalize(x)
-        return self.map(x)
+        mods = list(self.map)
+        i = 0
+        while i < len(mods):
+            fuse = isinstance(mods[i], MapLinear) and i + 1 < len(mods) and isinstance(mods[i + 1], nn.LeakyReLU)
+            if fuse:
+                x = mods[i](x, slope=mods[i + 1].negative_slope)      # linear * lr -> lrelu in one kernel
+                i += 2
+            else:
+                x = mods[i](x)
+                i += 1
+        return x
 
 
 class Synthesis(nn.Module):
@@ -370,9 +383,7 @@ class Discriminator(nn.Module):
                 x = C.conv2d_bias_act(x, m.layer.weight, m.layer.bias, m.coef, SLOPE if fuse else None)
                 i += 2 if fuse else 1
             elif isinstance(m, ELR):
-                x = m(x)
-                if fuse:
-                    x = F.leaky_relu(x, SLOPE)
+                x = linear_bias_act(x, m.layer.weight, m.layer.bias, m.coef, 1.0, SLOPE if fuse else None)
                 i += 2 if fuse else 1
             else:
                 x = m(x)

@@ -17,8 +17,12 @@ import torch
 
 from .. import _lib
 
+import os
+
 IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC32, IMPL_HALO, IMPL_HALO32 = 0, 1, 2, 3, 4, 5
-_default_impl = IMPL_AUTO
+_default_impl = int(os.environ.get('SG2_CONV_IMPL', '0'))     # 0 = auto; see set_default_impl
+# experiment switch (profiles/r2_*): data-gradient / second-order convolutions on the fp32-class kernel instead of bf16x3
+_grad_precise = os.environ.get('SG2_GRAD_PRECISE', '0') == '1'
 
 # bench.py sets this to a list to time every convolution launch with CUDA events on the launching stream:
 # entries are (kind, flops, start_event, end_event).  None = no timing (the default).
@@ -80,7 +84,7 @@ def _pack(w: torch.Tensor, coef: float, transpose: bool, impl: int) -> torch.Ten
 
 
 def _conv_raw(x, w, coef, transpose, in_scale=None, out_scale=None, bias=None, noise=None,
-              slope=None, out_nchw=False, impl=None, precise=None):
+              slope=None, out_nchw=False, impl=None, precise=None, gain=1.0):
     """One library call: y = act(out_scale * conv(x * in_scale, w*coef) + bias + noise).
 
     transpose=True runs the data-gradient conv (x has w.shape[0] channels, y has w.shape[1]).
@@ -93,7 +97,7 @@ def _conv_raw(x, w, coef, transpose, in_scale=None, out_scale=None, bias=None, n
     co, ci, k, _ = w.shape
     cin, cout = (co, ci) if transpose else (ci, co)
     n, cx, h, wd = x.shape
-    precise = (not transpose) if precise is None else precise
+    precise = (not transpose or _grad_precise) if precise is None else (precise or _grad_precise)
     req = impl
     impl = lib.sg2_conv2d_select_impl(n, h, wd, cin, cout, k, req, 1 if precise else 0)
     if impl < 0 and not strict:
@@ -116,7 +120,7 @@ def _conv_raw(x, w, coef, transpose, in_scale=None, out_scale=None, bias=None, n
         _lib.check(lib.sg2_conv2d_fwd(
             x.data_ptr(), packed.data_ptr(), y.data_ptr(), _lib.strides4(y), n, h, wd, cin, cout, k,
             _lib.ptr(in_scale), _lib.ptr(out_scale), _lib.ptr(bias), _lib.ptr(noise),
-            3 if slope is not None else 1, float(slope if slope is not None else 0.0), 1.0,
+            3 if slope is not None else 1, float(slope if slope is not None else 0.0), float(gain),
             impl, _lib.stream_ptr(x)), 'sg2_conv2d_fwd')
     return y
 
@@ -292,9 +296,9 @@ def conv2d(x, w, coef: float = 1.0):
 
 class ConvBiasActFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, b, coef, slope):
-        y = _conv_raw(x, w, coef, False, bias=b, slope=slope)
-        ctx.coef, ctx.slope = coef, slope
+    def forward(ctx, x, w, b, coef, slope, gain=1.0):
+        y = _conv_raw(x, w, coef, False, bias=b, slope=slope, gain=gain)
+        ctx.coef, ctx.slope, ctx.gain = coef, slope, gain
         ctx.save_for_backward(x, w, y)
         return y
 
@@ -304,6 +308,8 @@ class ConvBiasActFn(torch.autograd.Function):
         x, w, y = ctx.saved_tensors
         co = w.shape[0]
         gb = None
+        if ctx.gain != 1.0:
+            gy = gy * ctx.gain               # y = gain * lrelu(t), gain > 0: sign(y) = sign(t), d y / d t = gain * lrelu'(y)
         if torch.is_grad_enabled() or co % 4 != 0:
             # create_graph (R1): every piece must stay differentiable
             gu = act_grad(gy, y, ctx.slope) if ctx.slope is not None else gy
@@ -321,7 +327,7 @@ class ConvBiasActFn(torch.autograd.Function):
                 gup, gb, _ = _bwd_prep_planes(gy, y, ctx.slope)
                 gx = _conv_planes(gup, w, ctx.coef, True) if need_gx else None
                 gw = _wgrad_planes(_split_planes(x), gup, k, ctx.coef) if need_gw else None
-                return gx, gw, (gb if ctx.needs_input_grad[2] else None), None, None
+                return gx, gw, (gb if ctx.needs_input_grad[2] else None), None, None, None
             # first-order backward: leaky-ReLU mask and the bias-gradient reduction in ONE pass over (gy, y)
             lib = _lib.load()
             gyc = _cl(gy)
@@ -342,13 +348,15 @@ class ConvBiasActFn(torch.autograd.Function):
             gx = Conv2dTransposeFn.apply(gu, w, ctx.coef)
         if ctx.needs_input_grad[1]:
             gw = Conv2dWgradFn.apply(x, gu, w.shape[2], ctx.coef)
-        return gx, gw, (gb if ctx.needs_input_grad[2] else None), None, None
+        return gx, gw, (gb if ctx.needs_input_grad[2] else None), None, None, None
 
 
-def conv2d_bias_act(x, w, b, coef: float = 1.0, slope: float | None = 0.2):
-    """lrelu_slope(conv2d(x * coef, w) + b): Conv2d('elr') + LeakyReLU (model.py:50-53, 191-193).
+def conv2d_bias_act(x, w, b, coef: float = 1.0, slope: float | None = 0.2, gain: float = 1.0):
+    """gain * lrelu_slope(conv2d(x * coef, w) + b): Conv2d('elr') + LeakyReLU (model.py:50-53, 191-193); with gain = the
+    bias_act gain of the StyleGAN3-style ConvAct (implementations/StyleGAN3/model.py:411-416).
     slope=None -> no activation (the DBlock skip conv, model.py:201)."""
-    return ConvBiasActFn.apply(x, w, b, float(coef), slope)
+    assert gain > 0
+    return ConvBiasActFn.apply(x, w, b, float(coef), slope, float(gain))
 
 
 # ----------------------------------------------------------------------------------------------

@@ -229,6 +229,37 @@ int sg2_conv2d_wgrad_planes(const void* x_planes, const void* gy_planes, float* 
                             int n, int h, int w, int ci, int co, int k, float coef, int accumulate,
                             sg2_stream_t stream);
 
+/* fully connected layers ------------------------------------------------------ *
+ * replaces: nn.Linear inside ELR (implementations/StyleGAN2/model.py:29-37, 44-47) = ATen addmm (cuBLAS) -- the 8
+ *           MapLinear + LeakyReLU of Mapping (:71-78, 263-282), ModulatedConv2d.affine (:102, 110), the discriminator
+ *           epilogue Linear(8192,512) -> LeakyReLU -> Linear(512,1) (:392-396) -- and PixelNorm (:253-256).
+ * x [B,K], w [N,K] (nn.Linear layout), bias [N] or NULL, y [B,N]; all dense fp32.  slope = 1 means "no activation".
+ *   fwd:        y  = lrelu_slope( gain * (coef * x W^T + bias) )
+ *   bwd_data:   gx = coef * gu W,      gu = gy * gain * (y > 0 ? 1 : slope); y NULL -> gu = gy * gain
+ *   bwd_weight: gw = coef * gu^T x,    gb = sum_b gu (gb may be NULL)
+ * With bias = NULL, gain = 1, slope = 1, y = NULL the three calls are F(x,W) = x W^T, Dx(g,W) = g W, Dw(g,x) = g^T x:
+ * a family closed under differentiation (what R1's double backward through the epilogue uses).  No atomics.
+ *   pixelnorm:  y = x / (sqrt(mean_k x^2) + eps)                                                                  */
+int sg2_linear_fwd(const float* x, const float* w, const float* bias, float* y, int B, int K, int N,
+                   float coef, float gain, float slope, sg2_stream_t stream);
+int sg2_linear_bwd_data(const float* gy, const float* y, const float* w, float* gx, int B, int K, int N,
+                        float coef, float gain, float slope, sg2_stream_t stream);
+int sg2_linear_bwd_weight(const float* gy, const float* y, const float* x, float* gw, float* gb, int B, int K, int N,
+                          float coef, float gain, float slope, sg2_stream_t stream);
+int sg2_pixelnorm(const float* x, float* y, int B, int K, float eps, sg2_stream_t stream);
+
+/* DiffAugment ------------------------------------------------------------------ *
+ * replaces: thirdparty/diffaugment/DiffAugment.py:10-77 with policy a subset of 'color,translation,cutout' in that order
+ *           (the training step uses 'color,translation': implementations/StyleGAN2/utils.py:63-68,92) -- one pass instead of
+ *           ~10.  x, y [B,C,H,W] dense NCHW fp32, C <= 8.  rb/rs/rc: [B] raw U[0,1) draws (DiffAugment.py:24,30,36) or NULL;
+ *           ty/tx: [B] int64 shifts (:42-43) or NULL; cy/cx: [B] int64 cut-out offsets (:58-59) or NULL with the window
+ *           size cut_h x cut_w.  backward = 1 applies the transpose (x = gy, y = gx); linear_only = 1 drops the brightness
+ *           constant (the derivative of the map).  workspace: sg2_diffaugment_workspace bytes.  Deterministic.        */
+int64_t sg2_diffaugment_workspace(int B, int H, int W);
+int sg2_diffaugment(const float* x, float* y, const float* rb, const float* rs, const float* rc,
+                    const int64_t* ty, const int64_t* tx, const int64_t* cy, const int64_t* cx, int cut_h, int cut_w,
+                    int B, int C, int H, int W, int backward, int linear_only, void* workspace, sg2_stream_t stream);
+
 /* optimizer ---------------------------------------------------------------- *
  * replaces: torch.optim.Adam.step (implementations/StyleGAN2/utils.py:220-221,
  *           85-86,112-113; ~125 per-tensor launches) over ONE flat fp32 buffer,
