@@ -61,6 +61,9 @@ SIGNATURES = {
     'sg2_pixelnorm': (_int, [_vp, _vp, _int, _int, _f, _vp]),
     'sg2_diffaugment_workspace': (_i64, [_int, _int, _int]),
     'sg2_diffaugment': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int, _int, _vp, _vp]),
+    'sg2_reflect_pad': (_int, [_vp, _vp, _i64, _int, _int, _int, _int, _int, _int, _int, _vp]),
+    'sg2_affine_sample': (_int, [_vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int, _vp]),
+    'sg2_color_affine': (_int, [_vp, _vp, _vp, _int, _i64, _int, _vp]),
     'sg2_ema_update': (_int, [_vp, _vp, _i64, _f, _vp]),
     'sg2_counter_add': (_int, [_vp, _int, _int, _int, _int, _vp]),
     'sg2_adam_multi': (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _int, _f, _f, _f, _f, _f, _vp]),
@@ -112,6 +115,13 @@ def require_cuda(*tensors):
 
 
 DTYPE_CODE = {torch.float32: 0, torch.float16: 1, torch.float64: 2}
+
+
+# Autocast (the reference's default run mode is fp16 autocast + GradScaler: implementations/StyleGAN2/utils.py:47,62,167,
+# utils/argument.py:25): every custom autograd Function of this package takes its tensors as float32 -- inside an
+# autocast region incoming half tensors are cast up and the kernels compute and store fp32 ("AMP-compatible, fp32 compute").
+amp_fwd = torch.amp.custom_fwd(device_type='cuda', cast_inputs=torch.float32)
+amp_bwd = torch.amp.custom_bwd(device_type='cuda')
 
 
 def launch_count() -> int:

@@ -19,50 +19,73 @@
 namespace sg2 {
 namespace lin {
 
-constexpr int RB = 16;          // batch rows per register block
 
-// one warp per output feature n; lanes stride k
-__global__ void __launch_bounds__(128) linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+// CTA = 16 output features (8 warps x 2) x all batch rows; the x tile [32 rows][256 k] is staged in shared memory so x is read
+// once per CTA (not once per feature) and every weight row once per 32 batch rows; lanes stride k with 128-bit loads
+constexpr int FWD_NT = 16, FWD_RB = 32, FWD_KC = 256;
+
+__global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                                          float* __restrict__ y, int B, int K, int N, float coef, float gain, float slope) {
-    const int lane = threadIdx.x & 31;
-    const int n = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (n >= N) return;
-    const float* wr = w + (long long)n * K;
+    __shared__ __align__(16) float xs[FWD_RB][FWD_KC];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n0 = blockIdx.x * FWD_NT + warp * 2;
     const bool vec = (K & 3) == 0 && (((uintptr_t)x | (uintptr_t)w) & 15) == 0;
-    for (int b0 = 0; b0 < B; b0 += RB) {
-        float acc[RB];
+    for (int b0 = 0; b0 < B; b0 += FWD_RB) {
+        const int rows = min(FWD_RB, B - b0);
+        float acc[2][FWD_RB];
 #pragma unroll
-        for (int r = 0; r < RB; ++r) acc[r] = 0.f;
-        const int rows = min(RB, B - b0);
-        if (vec) {
-            for (int k = lane * 4; k < K; k += 128) {
-                const float4 wv = ldg4(wr + k);
+        for (int r = 0; r < FWD_RB; ++r) acc[0][r] = acc[1][r] = 0.f;
+        for (int k0 = 0; k0 < K; k0 += FWD_KC) {
+            const int kc = min(FWD_KC, K - k0);
+            __syncthreads();
+            if (vec) {
+                for (int i = threadIdx.x; i < FWD_RB * (FWD_KC / 4); i += 256) {
+                    const int r = i / (FWD_KC / 4), c4 = (i % (FWD_KC / 4)) * 4;
+                    float4 v = f4zero();
+                    if (r < rows && c4 < kc) v = ldg4(x + (long long)(b0 + r) * K + k0 + c4);
+                    *reinterpret_cast<float4*>(&xs[r][c4]) = v;
+                }
+            } else {
+                for (int i = threadIdx.x; i < FWD_RB * FWD_KC; i += 256) {
+                    const int r = i / FWD_KC, c = i % FWD_KC;
+                    xs[r][c] = (r < rows && c < kc) ? __ldg(x + (long long)(b0 + r) * K + k0 + c) : 0.f;
+                }
+            }
+            __syncthreads();
 #pragma unroll
-                for (int r = 0; r < RB; ++r) {
-                    if (r < rows) {
-                        const float4 xv = ldg4(x + (long long)(b0 + r) * K + k);
-                        acc[r] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, fmaf(xv.z, wv.z, fmaf(xv.w, wv.w, acc[r]))));
+            for (int f = 0; f < 2; ++f) {
+                const int n = n0 + f;
+                if (n >= N) continue;
+                const float* wr = w + (long long)n * K + k0;
+                for (int c = lane * 4; c < kc; c += 128) {
+                    float4 wv;
+                    if (vec) wv = ldg4(wr + c);
+                    else {
+                        wv.x = __ldg(wr + c); wv.y = c + 1 < kc ? __ldg(wr + c + 1) : 0.f;
+                        wv.z = c + 2 < kc ? __ldg(wr + c + 2) : 0.f; wv.w = c + 3 < kc ? __ldg(wr + c + 3) : 0.f;
+                    }
+#pragma unroll
+                    for (int r = 0; r < FWD_RB; ++r) {
+                        const float4 xv = *reinterpret_cast<const float4*>(&xs[r][c]);
+                        acc[f][r] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, fmaf(xv.z, wv.z, fmaf(xv.w, wv.w, acc[f][r]))));
                     }
                 }
             }
-        } else {
-            for (int k = lane; k < K; k += 32) {
-                const float wv = __ldg(wr + k);
+        }
 #pragma unroll
-                for (int r = 0; r < RB; ++r)
-                    if (r < rows) acc[r] = fmaf(__ldg(x + (long long)(b0 + r) * K + k), wv, acc[r]);
+        for (int f = 0; f < 2; ++f) {
+            const int n = n0 + f;
+            float mine = 0.f;
+#pragma unroll
+            for (int r = 0; r < FWD_RB; ++r) {
+                const float sum = warp_sum(acc[f][r]);
+                if (lane == r) mine = sum;
             }
-        }
-        float mine = 0.f;
-#pragma unroll
-        for (int r = 0; r < RB; ++r) {
-            const float s = warp_sum(acc[r]);
-            if (lane == r) mine = s;
-        }
-        if (lane < rows) {
-            float t = (coef * mine + (bias ? __ldg(bias + n) : 0.f)) * gain;
-            t = t > 0.f ? t : t * slope;
-            y[(long long)(b0 + lane) * N + n] = t;
+            if (n < N && lane < rows) {
+                float t = (coef * mine + (bias ? __ldg(bias + n) : 0.f)) * gain;
+                t = t > 0.f ? t : t * slope;
+                y[(long long)(b0 + lane) * N + n] = t;
+            }
         }
     }
 }
@@ -177,7 +200,7 @@ extern "C" int sg2_linear_fwd(const float* x, const float* w, const float* bias,
                               float coef, float gain, float slope, sg2_stream_t stream) {
     SG2_REQUIRE(x && w && y, "linear_fwd: null pointer");
     SG2_REQUIRE(B > 0 && K > 0 && N > 0, "linear_fwd: empty tensor");
-    lin::linear_fwd_kernel<<<(unsigned)ceil_div(N, 4), 128, 0, (cudaStream_t)stream>>>(x, w, bias, y, B, K, N, coef, gain, slope);
+    lin::linear_fwd_kernel<<<(unsigned)ceil_div(N, lin::FWD_NT), 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, B, K, N, coef, gain, slope);
     return launched("linear_fwd");
 }
 

@@ -13,6 +13,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib, rng
+from ._lib import amp_bwd, amp_fwd
 
 _CANON = ('color', 'translation', 'cutout')
 
@@ -55,11 +56,13 @@ class _AugFn(torch.autograd.Function):
     """y = A x + c (the fused policy); linear_only drops c (that is the derivative of the backward op below)."""
 
     @staticmethod
+    @amp_fwd
     def forward(ctx, x, d, linear_only):
         ctx.d = d
         return _launch(x, d, False, linear_only)
 
     @staticmethod
+    @amp_bwd
     def backward(ctx, gy):
         return _AugTFn.apply(gy, ctx.d), None, None
 
@@ -68,11 +71,13 @@ class _AugTFn(torch.autograd.Function):
     """gx = A^T gy"""
 
     @staticmethod
+    @amp_fwd
     def forward(ctx, gy, d):
         ctx.d = d
         return _launch(gy, d, True, False)
 
     @staticmethod
+    @amp_bwd
     def backward(ctx, ggx):
         return _AugFn.apply(ggx, ctx.d, True), None
 

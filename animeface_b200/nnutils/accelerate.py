@@ -108,6 +108,25 @@ class AllReduceOptimizer(optim.Optimizer):
         self._optimizer.load_state_dict(sd)
 
 
+class ScaledFlatAdam:
+    """FlatAdam behind a GradScaler (amp=True): exchange the scaled gradients first, then let the scaler unscale them,
+    check them for infs (every rank sees the same reduced values, so every rank takes the same decision) and step."""
+
+    def __init__(self, optimizer: FlatAdam, scaler):
+        self._optimizer, self._scaler = optimizer, scaler
+
+    def step(self, closure=None):
+        assert closure is None
+        self._optimizer.reduce_gradients()
+        self._scaler.step(self._optimizer)
+
+    def zero_grad(self, set_to_none=True):
+        self._optimizer.zero_grad(set_to_none)
+
+    def __getattr__(self, name):
+        return getattr(self._optimizer, name)
+
+
 class DataLoaderWrapper(DataLoader):
     """Moves every batch to the device (reference accelerate.py:98-132)."""
 
@@ -214,7 +233,8 @@ class MiniAccelerator:
 
     def _prepare_optimizer(self, optimizer):
         if isinstance(optimizer, FlatAdam):
-            return optimizer                     # all-reduce is fused into its step
+            # all-reduce is fused into its step; behind a GradScaler the exchange has to come before the scaler's inf check
+            return ScaledFlatAdam(optimizer, self._scaler) if self._scaler is not None else optimizer
         if self._scaler is not None or _world() > 1:
             return AllReduceOptimizer(optimizer, self._scaler)
         return optimizer

@@ -124,6 +124,25 @@ class FlatAdam(torch.optim.Optimizer):
     def zero_grad(self, set_to_none: bool = True):
         for p in self._ps:
             p.grad = None
+        self._reduced = False
+
+    @torch.no_grad()
+    def reduce_gradients(self):
+        """Pack the gradients into the flat buffer, all-reduce it (mean over ranks) and re-point every ``p.grad`` at its view
+        of the reduced buffer.  ``step()`` then skips its own exchange.  This is the order a GradScaler needs
+        (implementations/StyleGAN2/utils.py:85,112 run ``optimizer.step()`` through the scaler): the ranks must agree on the
+        scaler's inf check, so it has to look at the REDUCED gradients (``MiniAccelerator`` wires this up when amp=True)."""
+        present = [i for i, p in enumerate(self._ps) if p.grad is not None]
+        if not present or getattr(self, '_reduced', False):
+            return
+        self._check_views()
+        torch._foreach_copy_([self._gviews[i] for i in present], [self._ps[i].grad for i in present])
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self._G)
+            self._G.mul_(1.0 / dist.get_world_size())
+        for i in present:
+            self._ps[i].grad = self._gviews[i]
+        self._reduced = True
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -134,11 +153,14 @@ class FlatAdam(torch.optim.Optimizer):
         if not present:
             return
         self._check_views()
-        torch._foreach_copy_([self._gviews[i] for i in present], [self._ps[i].grad for i in present])
         scale = 1.0
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self._G)                      # the one collective of the step
-            scale = 1.0 / dist.get_world_size()
+        if getattr(self, '_reduced', False):
+            self._reduced = False                         # reduce_gradients() already packed / exchanged / averaged
+        else:
+            torch._foreach_copy_([self._gviews[i] for i in present], [self._ps[i].grad for i in present])
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                dist.all_reduce(self._G)                  # the one collective of the step
+                scale = 1.0 / dist.get_world_size()
         lib = _lib.load()
         st = _lib.stream_ptr(self._P)
         # presence flags from plain integer ranges (no host->device copy: the call replays inside a CUDA graph)

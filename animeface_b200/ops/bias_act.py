@@ -14,6 +14,7 @@ from dataclasses import dataclass
 import torch
 
 from .. import _lib
+from .._lib import amp_bwd, amp_fwd
 
 
 class _Spec(dict):
@@ -105,6 +106,7 @@ def _other_dims(t, dim):
 
 class _BiasActFn(torch.autograd.Function):
     @staticmethod
+    @amp_fwd
     def forward(ctx, x, b, cfg: _Cfg):
         x = _dense(x)
         b = None if b is None else b.contiguous()
@@ -119,6 +121,7 @@ class _BiasActFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @amp_bwd
     def backward(ctx, dy):
         x, b, y = ctx.saved_tensors
         cfg = ctx.cfg
@@ -134,6 +137,7 @@ class _BiasActGradFn(torch.autograd.Function):
     """dx = dy * act'(.) * gain (masked by the clamp), from the saved output y (or x for swish)."""
 
     @staticmethod
+    @amp_fwd
     def forward(ctx, dy, x, b, y, cfg: _Cfg):
         ref = y if y is not None else x
         dy = _like(dy, ref)
@@ -143,6 +147,7 @@ class _BiasActGradFn(torch.autograd.Function):
         return dx
 
     @staticmethod
+    @amp_bwd
     def backward(ctx, d_dx):
         dy, x, b, y = ctx.saved_tensors
         cfg = ctx.cfg

@@ -16,6 +16,7 @@ from __future__ import annotations
 import torch
 
 from .. import _lib
+from .._lib import amp_bwd, amp_fwd
 
 import os
 
@@ -229,12 +230,14 @@ class Conv2dFn(torch.autograd.Function):
     """y = conv2d(x, w * coef), stride 1, same padding."""
 
     @staticmethod
+    @amp_fwd
     def forward(ctx, x, w, coef, precise=True):
         ctx.coef = coef
         ctx.save_for_backward(x, w)
         return _conv_raw(x, w, coef, False, precise=precise)
 
     @staticmethod
+    @amp_bwd
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
         gx = gw = None
@@ -249,12 +252,14 @@ class Conv2dTransposeFn(torch.autograd.Function):
     """gx = conv_transpose2d(gy, w * coef) (the data gradient of Conv2dFn)."""
 
     @staticmethod
+    @amp_fwd
     def forward(ctx, gy, w, coef):
         ctx.coef = coef
         ctx.save_for_backward(gy, w)
         return _conv_raw(gy, w, coef, True)
 
     @staticmethod
+    @amp_bwd
     def backward(ctx, g):
         gy, w = ctx.saved_tensors
         ggy = gw = None
@@ -269,12 +274,14 @@ class Conv2dWgradFn(torch.autograd.Function):
     """dw[co,ci,k,k] = coef * sum_{n,h,w} gy (x) x (the weight gradient of Conv2dFn)."""
 
     @staticmethod
+    @amp_fwd
     def forward(ctx, x, gy, k, coef):
         ctx.coef = coef
         ctx.save_for_backward(x, gy)
         return _wgrad_raw(x, gy, k, coef)
 
     @staticmethod
+    @amp_bwd
     def backward(ctx, gdw):
         x, gy = ctx.saved_tensors
         gx = ggy = None
@@ -296,6 +303,7 @@ def conv2d(x, w, coef: float = 1.0):
 
 class ConvBiasActFn(torch.autograd.Function):
     @staticmethod
+    @amp_fwd
     def forward(ctx, x, w, b, coef, slope, gain=1.0):
         y = _conv_raw(x, w, coef, False, bias=b, slope=slope, gain=gain)
         ctx.coef, ctx.slope, ctx.gain = coef, slope, gain
@@ -303,6 +311,7 @@ class ConvBiasActFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @amp_bwd
     def backward(ctx, gy):
         from .bias_act import act_grad
         x, w, y = ctx.saved_tensors
@@ -366,6 +375,7 @@ def conv2d_bias_act(x, w, b, coef: float = 1.0, slope: float | None = 0.2, gain:
 
 class ModConvFn(torch.autograd.Function):
     @staticmethod
+    @amp_fwd
     def forward(ctx, x, w, s, d, b, noise, coef, slope, out_nchw):
         y = _conv_raw(x, w, coef, False, in_scale=s, out_scale=d, bias=b, noise=noise, slope=slope, out_nchw=out_nchw)
         ctx.coef, ctx.slope, ctx.out_nchw = coef, slope, out_nchw
@@ -376,6 +386,7 @@ class ModConvFn(torch.autograd.Function):
 
     @staticmethod
     @torch.autograd.function.once_differentiable
+    @amp_bwd
     def backward(ctx, gy):
         lib = _lib.load()
         x, w, s, d, b, noise, y = ctx.saved_tensors

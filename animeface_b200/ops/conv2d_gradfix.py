@@ -5,11 +5,12 @@ Reference: thirdparty/stylegan3_ops/ops/conv2d_gradfix.py (``conv2d`` :29, ``con
 lands on the closed convolution family of ``ops.conv2d`` (forward conv, data-gradient conv, weight gradient -- each one's
 backward written with the other two), so the same property holds on the libsg2b200 kernels.
 
-Supported: groups = 1, dilation = 1, square odd kernels k in {1, 3}.  The library convolves with stride 1 and 'same'
-padding; other stride / padding combinations are expressed around it -- a larger padding pads the input first, a smaller
-one crops the 'same' result, a stride keeps every stride-th sample.  (A strided launch is round-2 work: today the
-stride-2 convolutions of the StyleGAN3-style discriminator pay 4x their flops.)  ``conv_transpose2d`` is only used by the
-up-sampling branch of ``conv2d_resample`` (StyleGAN3 generator) and is not built.
+Supported: dilation = 1, square odd kernels k in {1, 3}, any stride / padding / groups.  The library convolves with stride 1
+and 'same' padding; everything else is expressed around that call with ops that are themselves differentiable to any
+order -- a larger padding pads the input first, a smaller one crops the 'same' result, a stride keeps every stride-th
+sample, groups run group by group, and the transposed convolution is zero insertion (``upfirdn2d`` with up = stride and no
+filter, which also applies the padding / cropping) followed by a correlation with the transposed, tap-flipped weight.
+(The strided cases pay stride^2 times their flops; they are off the BASELINE config 2 hot path.)
 """
 from __future__ import annotations
 
@@ -43,8 +44,13 @@ def _pair(v):
 def conv2d(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
     """torch.nn.functional.conv2d semantics (cross-correlation), reference signature conv2d_gradfix.py:29."""
     assert isinstance(input, torch.Tensor) and input.ndim == 4 and weight.ndim == 4
-    if groups != 1 or _pair(dilation) != (1, 1):
-        raise NotImplementedError('conv2d_gradfix.conv2d: groups = 1 and dilation = 1 only')
+    if _pair(dilation) != (1, 1):
+        raise NotImplementedError('conv2d_gradfix.conv2d: dilation = 1 only')
+    if groups != 1:
+        assert input.shape[1] % groups == 0 and weight.shape[0] % groups == 0 and weight.shape[1] * groups == input.shape[1]
+        xs, ws = input.chunk(groups, dim=1), weight.chunk(groups, dim=0)
+        bs = bias.chunk(groups, dim=0) if bias is not None else [None] * groups
+        return torch.cat([conv2d(x_, w_, b_, stride, padding, dilation, 1) for x_, w_, b_ in zip(xs, ws, bs)], dim=1)
     co, ci, kh, kw = weight.shape
     if kh != kw or kh not in (1, 3):
         raise NotImplementedError('conv2d_gradfix.conv2d: square kernels of size 1 or 3 only')
@@ -67,5 +73,31 @@ def conv2d(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
 
 
 def conv_transpose2d(input, weight, bias=None, stride=1, padding=0, output_padding=0, groups=1, dilation=1):
-    raise NotImplementedError('conv2d_gradfix.conv_transpose2d (the up-sampling branch of conv2d_resample) is not built: '
-                              'it belongs to the StyleGAN3 generator, SURVEY 8f n3')
+    """torch.nn.functional.conv_transpose2d semantics, reference signature conv2d_gradfix.py:34.
+    input [N, Ci, H, W], weight [Ci, Co / groups, k, k]; out size (H - 1) * stride - 2 * padding + k + output_padding."""
+    from . import upfirdn2d as U
+    assert isinstance(input, torch.Tensor) and input.ndim == 4 and weight.ndim == 4
+    if _pair(dilation) != (1, 1):
+        raise NotImplementedError('conv2d_gradfix.conv_transpose2d: dilation = 1 only')
+    if groups != 1:
+        assert input.shape[1] % groups == 0 and weight.shape[0] == input.shape[1]
+        xs, ws = input.chunk(groups, dim=1), weight.chunk(groups, dim=0)
+        y = torch.cat([conv_transpose2d(x_, w_, None, stride, padding, output_padding, 1, dilation) for x_, w_ in zip(xs, ws)], dim=1)
+        return y if bias is None else y + bias.reshape(1, -1, 1, 1)
+    ci, co, kh, kw = weight.shape
+    if kh != kw or kh not in (1, 3):
+        raise NotImplementedError('conv2d_gradfix.conv_transpose2d: square kernels of size 1 or 3 only')
+    sy, sx = _pair(stride)
+    py, px = _pair(padding)
+    oy, ox = _pair(output_padding)
+    assert sy >= 1 and sx >= 1 and py >= 0 and px >= 0 and 0 <= oy < max(sy, 2) and 0 <= ox < max(sx, 2)
+    if weight_gradients_disabled:
+        weight = weight.detach()
+    # zero insertion leaves the samples at 0, s, 2s, ... of a length H*s signal (s - 1 trailing zeros); the full correlation
+    # needs k - 1 - p zeros in front and k - 1 - p + output_padding behind the LAST sample: negative amounts crop
+    fy, fx = kh - 1 - py, kw - 1 - px
+    pads = [fx, fx - (sx - 1) + ox, fy, fy - (sy - 1) + oy]
+    if sy > 1 or sx > 1 or any(pads):
+        input = U.upfirdn2d(input, None, up=[sx, sy], padding=pads)
+    y = conv2d(input, weight.transpose(0, 1).flip([2, 3]), None, 1, 0)
+    return y if bias is None else y + bias.reshape(1, -1, 1, 1)

@@ -16,6 +16,7 @@ from __future__ import annotations
 import torch
 
 from .. import _lib
+from .._lib import amp_bwd, amp_fwd
 
 
 def _f32c(t):
@@ -69,12 +70,14 @@ class LinFn(torch.autograd.Function):
     """y = coef * x W^T"""
 
     @staticmethod
+    @amp_fwd
     def forward(ctx, x, w, coef):
         ctx.coef = coef
         ctx.save_for_backward(x, w)
         return _fwd_raw(x, w, None, coef, 1.0, None)
 
     @staticmethod
+    @amp_bwd
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
         gx = LinDxFn.apply(gy, w, ctx.coef) if ctx.needs_input_grad[0] else None
@@ -86,12 +89,14 @@ class LinDxFn(torch.autograd.Function):
     """gx = coef * g W"""
 
     @staticmethod
+    @amp_fwd
     def forward(ctx, g, w, coef):
         ctx.coef = coef
         ctx.save_for_backward(g, w)
         return _dx_raw(g, None, w, coef, 1.0, None)
 
     @staticmethod
+    @amp_bwd
     def backward(ctx, gout):
         g, w = ctx.saved_tensors
         gg = LinFn.apply(gout, w, ctx.coef) if ctx.needs_input_grad[0] else None
@@ -103,12 +108,14 @@ class LinDwFn(torch.autograd.Function):
     """gw = coef * g^T x"""
 
     @staticmethod
+    @amp_fwd
     def forward(ctx, g, x, coef):
         ctx.coef = coef
         ctx.save_for_backward(g, x)
         return _dw_raw(g, None, x, coef, 1.0, None, False)[0]
 
     @staticmethod
+    @amp_bwd
     def backward(ctx, gout):
         g, x = ctx.saved_tensors
         gg = LinFn.apply(x, gout, ctx.coef) if ctx.needs_input_grad[0] else None
@@ -121,6 +128,7 @@ class LinearBiasActFn(torch.autograd.Function):
     backward is composed from the closed family and the twice-differentiable activation gradient."""
 
     @staticmethod
+    @amp_fwd
     def forward(ctx, x, w, b, coef, gain, slope):
         y = _fwd_raw(x, w, b, coef, gain, slope)
         ctx.coef, ctx.gain, ctx.slope = coef, gain, slope
@@ -129,6 +137,7 @@ class LinearBiasActFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @amp_bwd
     def backward(ctx, gy):
         x, w, y = ctx.saved_tensors
         need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
@@ -155,6 +164,7 @@ def linear_bias_act(x, w, b=None, coef: float = 1.0, gain: float = 1.0, slope: f
 
 class PixelNormFn(torch.autograd.Function):
     @staticmethod
+    @amp_fwd
     def forward(ctx, x, eps):
         lib = _lib.load()
         _lib.require_cuda(x)
@@ -164,6 +174,7 @@ class PixelNormFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @amp_bwd
     def backward(ctx, gy):
         raise RuntimeError('pixel_norm: the fused kernel is for latents that do not require grad; use the composed expression')
 

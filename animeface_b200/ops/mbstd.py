@@ -11,6 +11,7 @@ from __future__ import annotations
 import torch
 
 from .. import _lib
+from .._lib import amp_bwd, amp_fwd
 
 
 def _resolve_groups(batch, group_size):
@@ -32,6 +33,7 @@ def _bwd_formula(x, gy, G, eps):
 
 class MbstdFn(torch.autograd.Function):
     @staticmethod
+    @amp_fwd
     def forward(ctx, x, G, eps):
         lib = _lib.load()
         _lib.require_cuda(x)
@@ -49,6 +51,7 @@ class MbstdFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @amp_bwd
     def backward(ctx, gy):
         x, = ctx.saved_tensors
         return MbstdGradFn.apply(x, gy, ctx.G, ctx.eps), None, None
@@ -56,6 +59,7 @@ class MbstdFn(torch.autograd.Function):
 
 class MbstdGradFn(torch.autograd.Function):
     @staticmethod
+    @amp_fwd
     def forward(ctx, x, gy, G, eps):
         lib = _lib.load()
         n, c, h, w = x.shape
@@ -67,6 +71,7 @@ class MbstdGradFn(torch.autograd.Function):
         return gx
 
     @staticmethod
+    @amp_bwd
     def backward(ctx, ggx):
         x, gy = ctx.saved_tensors
         outer = torch.is_grad_enabled()

@@ -12,6 +12,7 @@ from __future__ import annotations
 import torch
 
 from .. import _lib
+from .._lib import amp_bwd, amp_fwd
 from .conv2d import _cl, _empty_cl
 
 
@@ -48,22 +49,26 @@ def _up2x(x, scale, blur, adjoint):
 
 class Up2xFn(torch.autograd.Function):
     @staticmethod
+    @amp_fwd
     def forward(ctx, x, blur):
         ctx.blur = blur
         return _up2x(x, None, blur, False)
 
     @staticmethod
+    @amp_bwd
     def backward(ctx, gy):
         return Up2xAdjFn.apply(gy, ctx.blur), None
 
 
 class Up2xAdjFn(torch.autograd.Function):
     @staticmethod
+    @amp_fwd
     def forward(ctx, gy, blur):
         ctx.blur = blur
         return _up2x(gy, None, blur, True)
 
     @staticmethod
+    @amp_bwd
     def backward(ctx, g):
         return Up2xFn.apply(g, ctx.blur), None
 
@@ -99,11 +104,13 @@ class AvgPool2Fn(torch.autograd.Function):
     """y = alpha * (avg2x2(x) + avg2x2(t)); t may be None."""
 
     @staticmethod
+    @amp_fwd
     def forward(ctx, x, t, alpha):
         ctx.alpha, ctx.has_t = alpha, t is not None
         return _avgpool(x, t, alpha, False)
 
     @staticmethod
+    @amp_bwd
     def backward(ctx, gy):
         g = AvgPool2AdjFn.apply(gy, ctx.alpha)
         return g, (g if ctx.has_t else None), None
@@ -111,11 +118,13 @@ class AvgPool2Fn(torch.autograd.Function):
 
 class AvgPool2AdjFn(torch.autograd.Function):
     @staticmethod
+    @amp_fwd
     def forward(ctx, gy, alpha):
         ctx.alpha = alpha
         return _avgpool(gy, None, alpha, True)
 
     @staticmethod
+    @amp_bwd
     def backward(ctx, g):
         return AvgPool2Fn.apply(g, None, ctx.alpha), None
 

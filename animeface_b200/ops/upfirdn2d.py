@@ -16,6 +16,7 @@ from dataclasses import dataclass, replace
 import torch
 
 from .. import _lib
+from .._lib import amp_bwd, amp_fwd
 
 
 def _pair(v, what):
@@ -109,6 +110,7 @@ def _run(x: torch.Tensor, f2d: torch.Tensor, plan: _Plan) -> torch.Tensor:
 
 class _Upfirdn2dFn(torch.autograd.Function):
     @staticmethod
+    @amp_fwd
     def forward(ctx, x, f, plan: _Plan):
         assert isinstance(x, torch.Tensor) and x.ndim == 4
         _lib.require_cuda(x)
@@ -137,6 +139,7 @@ class _Upfirdn2dFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @amp_bwd
     def backward(ctx, dy):
         f, = ctx.saved_tensors
         assert not ctx.needs_input_grad[1], 'upfirdn2d: the filter is not differentiable'

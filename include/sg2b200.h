@@ -260,6 +260,23 @@ int sg2_diffaugment(const float* x, float* y, const float* rb, const float* rs, 
                     const int64_t* ty, const int64_t* tx, const int64_t* cy, const int64_t* cx, int cut_h, int cut_w,
                     int B, int C, int H, int W, int backward, int linear_only, void* workspace, sg2_stream_t stream);
 
+/* ADA augmentation pipeline -------------------------------------- *
+ * replaces: the ATen calls of thirdparty/ada/augment.py:115-427 that the StyleGAN2 step does not have --
+ *   torch.nn.functional.pad(mode='reflect') (:284), affine_grid + grid_sample_gradfix.grid_sample (:293-295; bilinear,
+ *   zeros padding, align_corners=False; thirdparty/stylegan3_ops/ops/grid_sample_gradfix.py:1-77), and the per-sample
+ *   colour matrix product (:352-361).  Dense NCHW fp32.  adjoint / transpose = 1 applies the exact adjoint (x = gy, y = gx);
+ *   every op is linear in the image, so forward and adjoint are each other's derivative.
+ * reflect_pad:   x [planes, h, w] -> y [planes, h + py0 + py1, w + px0 + px1]
+ * affine_sample: theta [n, 2, 3] maps normalised OUTPUT coordinates to normalised INPUT coordinates (F.affine_grid);
+ *                x [n,c,ih,iw] -> y [n,c,oh,ow]; the sampling grid is never materialised.  The adjoint scatters with fp32
+ *                atomics (as ATen's grid_sampler_2d_backward does).
+ * color_affine:  cmat [n, 4, 4] homogeneous colour transforms; x, y [n, 3, hw]: y = C[:3,:3] x + C[:3,3].            */
+int sg2_reflect_pad(const float* x, float* y, int64_t planes, int h, int w, int px0, int px1, int py0, int py1,
+                    int adjoint, sg2_stream_t stream);
+int sg2_affine_sample(const float* x, float* y, const float* theta, int n, int c, int ih, int iw, int oh, int ow,
+                      int adjoint, sg2_stream_t stream);
+int sg2_color_affine(const float* x, float* y, const float* cmat, int n, int64_t hw, int transpose, sg2_stream_t stream);
+
 /* optimizer ---------------------------------------------------------------- *
  * replaces: torch.optim.Adam.step (implementations/StyleGAN2/utils.py:220-221,
  *           85-86,112-113; ~125 per-tensor launches) over ONE flat fp32 buffer,

@@ -3,7 +3,7 @@ discriminator and of ``conv2d_resample`` for the down-sampling cases it uses.
 
 Only tests/ may import this.  Restated from (paths relative to the STomoya/animeface checkout):
   upfirdn2d        thirdparty/stylegan3_ops/ops/upfirdn2d.py:161-207 (_upfirdn2d_ref; up = 1 here)
-  conv2d_resample  thirdparty/stylegan3_ops/ops/conv2d_resample.py:40-137 (up = 1 branches)
+  conv2d_resample  thirdparty/stylegan3_ops/ops/conv2d_resample.py:40-141 (up = 1 fast paths; every case through the generic plan)
   bias_act         thirdparty/stylegan3_ops/ops/bias_act.py:86-115 (linear / lrelu)
   discriminator    implementations/StyleGAN3/model.py:16-30 (Linear), :382-510 (ConvAct, ResBlock, MinibatchStdDev,
                    DiscEpilogue, Discriminator)
@@ -51,6 +51,41 @@ def conv2d_resample(x, w, f=None, down=1, padding=0):
     if px0 == px1 and py0 == py1 and px0 >= 0 and py0 >= 0:
         return F.conv2d(x, w, padding=(py0, px0))
     return F.conv2d(upfirdn2d(x, None, 1, (px0, px1, py0, py1)), w)
+
+
+def upfirdn2d_full(x, f, up=1, down=1, padding=(0, 0, 0, 0), flip_filter=False, gain=1.0):
+    """thirdparty/stylegan3_ops/ops/upfirdn2d.py:161-207 (_upfirdn2d_ref) with up-sampling: zero-insert (samples at 0, up,
+    2 up, ...; up - 1 trailing zeros), pad / crop, true convolution with f * gain, keep every down-th sample."""
+    n, c, h, w_ = x.shape
+    if up > 1:
+        z = x.new_zeros(n, c, h, up, w_, up)
+        z[:, :, :, 0, :, 0] = x
+        x = z.reshape(n, c, h * up, w_ * up)
+    return upfirdn2d(x, f, down, padding, flip_filter, gain)
+
+
+def conv2d_resample_full(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True):
+    """thirdparty/stylegan3_ops/ops/conv2d_resample.py:40-141 through its generic plan (:125-129), which every fast path
+    must reproduce: zero-insert + low-pass (gain up^2) with all the padding in front, unpadded convolution, decimation."""
+    kh, kw = w.shape[2], w.shape[3]
+    fh, fw = (1, 1) if f is None else (f.shape[0], f.shape[1])
+    px0, px1, py0, py1 = (padding,) * 4 if isinstance(padding, int) else padding
+    if up > 1:
+        px0 += (fw + up - 1) // 2; px1 += (fw - up) // 2
+        py0 += (fh + up - 1) // 2; py1 += (fh - up) // 2
+    if down > 1:
+        px0 += (fw - down + 1) // 2; px1 += (fw - down) // 2
+        py0 += (fh - down + 1) // 2; py1 += (fh - down) // 2
+    x = upfirdn2d_full(x, f if up > 1 else None, up, 1, (px0, px1, py0, py1), False, up ** 2)
+    x = F.conv2d(x, w if flip_weight else w.flip([2, 3]), groups=groups)
+    if down > 1:
+        x = upfirdn2d_full(x, f, 1, down)
+    return x
+
+
+def conv_transpose2d(x, w, b=None, stride=1, padding=0, output_padding=0, groups=1):
+    """thirdparty/stylegan3_ops/ops/conv2d_gradfix.py:34-37 with enabled = False: the ATen op itself."""
+    return F.conv_transpose2d(x, w, b, stride=stride, padding=padding, output_padding=output_padding, groups=groups)
 
 
 def bias_act(x, b, act, gain):

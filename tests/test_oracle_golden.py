@@ -225,3 +225,25 @@ def test_sg3_discriminator_and_conv2d_resample(g_sg3d):
             assert bool(g['r1none.' + k]) or np.abs(ref).max() == 0, k
         else:
             assert rel_err(gr.numpy(), ref) < 2e-4 or np.abs(ref).max() < 1e-12, k
+
+
+def test_oracle_conv2d_resample_up_and_grouped_cases(g_resample):
+    """oracle/sg3d_torch.py (generic plan) against the reference's fast paths incl. gradients (tests/golden/resample.npz)."""
+    import ast
+    import torch
+    from oracle import sg3d_torch as S
+    g = g_resample
+    filt = dict(f4=torch.from_numpy(g['f4']), f6=torch.from_numpy(g['f6']))
+    for case in [ast.literal_eval(str(c)) for c in g['cr.cases']]:
+        name, ci, co, k, up, down, pad, fname, groups, flip_w = case
+        x = torch.from_numpy(g[f'cr.{name}.x']).requires_grad_(True)
+        w = torch.from_numpy(g[f'cr.{name}.w']).requires_grad_(True)
+        y = S.conv2d_resample_full(x, w, filt.get(fname), up, down, pad, groups, flip_w)
+        assert rel_err(y.detach().numpy(), g[f'cr.{name}.y']) < 2e-6, name
+        gx, gw = torch.autograd.grad(y, (x, w), torch.from_numpy(g[f'cr.{name}.gy']))
+        assert rel_err(gx.numpy(), g[f'cr.{name}.gx']) < 2e-6 and rel_err(gw.numpy(), g[f'cr.{name}.gw']) < 2e-6, name
+    for case in [ast.literal_eval(str(c)) for c in g['ct.cases']]:
+        name, ci, co, k, stride, pad, opad, groups = case
+        x, w, b = (torch.from_numpy(g[f'ct.{name}.{t}']) for t in 'xwb')
+        y = S.conv_transpose2d(x, w, b, stride, pad, opad, groups)
+        assert rel_err(y.numpy(), g[f'ct.{name}.y']) < 1e-6, name
