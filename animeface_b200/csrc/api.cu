@@ -28,9 +28,10 @@ extern "C" const char* sg2_last_error(void) { return g_err; }
 extern "C" int64_t sg2_launch_count(void) { return (int64_t)g_launches.load(); }
 extern "C" int sg2_debug_trace(void* device_buf) { g_trace = (long long*)device_buf; return SG2_OK; }
 
-// The packed buffer always starts with a 16-byte header {impl, transpose, co, ci} so a mismatched
-// pack/conv pair is caught instead of silently computing garbage.
-struct PackHeader { int impl, transpose, co, ci; };
+// The packed image starts 256 bytes into the buffer (reserved, keeps the TMA source 256-byte aligned whatever the allocator
+// returns).  Round 1 launched a one-thread kernel per pack to write a {impl, transpose, co, ci} header there that nothing ever
+// read back -- ~1000 launches per 7 steps (profiles/r2e_launches.txt); the pack/conv pairing is checked on the host instead
+// (callers resolve the implementation once with sg2_conv2d_select_impl and pass the same code to both).
 
 extern "C" int sg2_conv2d_select_impl(int n, int h, int w, int ci, int co, int k, int impl, int precise) {
     if (n <= 0 || h <= 0 || w <= 0 || ci <= 0 || co <= 0 || (k != 1 && k != 3) || impl < 0 || impl > 5) return SG2_EINVAL;
@@ -56,8 +57,6 @@ static int pick_impl_for_pack(int co, int ci, int k, int transpose, int impl) {
     return resolve_impl(impl, transpose ? 0 : 1, 1, 16, 16, cin, cout, k);
 }
 
-__global__ void write_header_kernel(PackHeader* h, PackHeader v) { *h = v; }
-
 extern "C" int sg2_conv2d_pack_weight(const float* w, void* packed, int co, int ci, int k,
                                       float coef, int transpose, int impl, sg2_stream_t stream) {
     SG2_REQUIRE(w && packed, "conv2d_pack_weight: null pointer");
@@ -65,10 +64,6 @@ extern "C" int sg2_conv2d_pack_weight(const float* w, void* packed, int co, int 
     const int use = pick_impl_for_pack(co, ci, k, transpose, impl);
     if (use < 0) return fail(SG2_ENOTSUP, "conv2d_pack_weight: tcgen05 path does not take co=%d ci=%d k=%d", co, ci, k);
     cudaStream_t st = (cudaStream_t)stream;
-    PackHeader hv{use, transpose ? 1 : 0, co, ci};
-    write_header_kernel<<<1, 1, 0, st>>>((PackHeader*)packed, hv);
-    int rc = launched("pack_header");
-    if (rc) return rc;
     void* body = (char*)packed + 256;
     if (use == 1) return conv_pack_simt(w, (float*)body, co, ci, k, coef, transpose, st);
     if (use == 3) return conv_pack_tc32(w, body, co, ci, k, coef, transpose, st);

@@ -56,6 +56,14 @@ template <int BN, bool PRECISE> struct Cfg {
     static constexpr int ACC_COLS = 2 * BN;
     static constexpr int NACC = 512 / ACC_COLS >= 4 ? 4 : 512 / ACC_COLS;       // buffers: promotion / epilogue latency hides behind NACC-1 segments
     static constexpr uint32_t TMEM_COLS = NACC * ACC_COLS;
+    // BN = 128, fp32-class: promotion is bound by the TMEM read bandwidth (a [D1|D2] segment is 128 KB), not by the MMAs.  Only
+    // D1 (big*big, whose chain length decides the error) needs promoting every few taps; the cross terms are 2^-11 of the result
+    // and can accumulate over the whole tile.  Layout [D1_a | D2_x | D1_b | D2_y]: the D1 buffers alternate per segment, the D2
+    // buffers per TILE (so reading D2 at the end of a tile overlaps the next tile's MMAs): TMEM reads drop from 128 KB to
+    // 64 KB per segment + 64 KB per tile.  The wide MMA A0 x [B0 ; B1] needs D2 right behind D1 -- true for (D1_a, D2_x) and
+    // (D1_b, D2_y); the other two pairings, and the first k16 step of every segment (D1 restarts, D2 continues), issue the three
+    // products as three N = BN instructions.
+    static constexpr bool D2X = PRECISE && BN == 128;
 };
 
 struct Params {
@@ -96,6 +104,7 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
     auto acc_full = [&](int b) { return bar_base + 160u + 8u * b; };          // NACC <= 4
     auto acc_empty = [&](int b) { return bar_base + 192u + 8u * b; };         // NACC <= 4
     const uint32_t tmem_slot = bar_base + 224u;
+    auto d2_empty = [&](int b) { return bar_base + 232u + 8u * b; };          // 2 (D2X only)
     auto plane = [&](int buf, int pl) { return plane_base + (uint32_t)((buf * 2 + pl) * PLANE_PITCH); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -122,6 +131,7 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
         }
         for (int s = 0; s < C::NACC; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), C::EPI_WARPS); }
         for (int s = 0; s < BSTAGES; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        for (int s = 0; s < 2; ++s) mbar_init(d2_empty(s), C::EPI_WARPS);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
@@ -170,10 +180,12 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
         if (elect_one()) {
             constexpr uint32_t idesc = PRECISE ? idesc_f16(BM, BN) : idesc_bf16(BM, BN);              // N = BN
             constexpr uint32_t idesc2 = PRECISE ? idesc_f16(BM, 2 * BN) : idesc_bf16(BM, 2 * BN);     // N = 2 BN (both weight planes)
-            int bt = 0, kbg = 0, sg = 0;                  // global weight-tile / channel-block / accumulator-segment counters
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int bt = 0, kbg = 0, sg = 0, tcount = 0;      // global weight-tile / channel-block / accumulator-segment / tile counters
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
                 int f = 0, fseg = 0;                      // flat (kb, tap) index inside the tile / inside the accumulator segment
                 const int nflat = p.nkb * taps;
+                const int tp = tcount & 1;                // D2X: which D2 buffer this tile accumulates its cross terms in
+                if (C::D2X) mbar_wait_t(d2_empty(tp), ((tcount >> 1) & 1) ^ 1, tr, w2);
                 for (int kb = 0; kb < p.nkb; ++kb, ++kbg) {
                     const int pbuf = kbg & 1;
                     mbar_wait_t(pl_full(pbuf), (kbg >> 1) & 1, tr, w0);
@@ -187,16 +199,34 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
                         const int s = bt % BSTAGES;
                         mbar_wait_t(b_full(s), (bt / BSTAGES) & 1, tr, w1);
                         tc_fence_after();
-                        const uint32_t d = tmem_d + (uint32_t)(abuf * C::ACC_COLS);
                         const uint32_t arow = (uint32_t)(dy * PW + dx) * 16u;
                         const uint32_t a0 = plane(pbuf, 0) + arow, a1 = plane(pbuf, 1) + arow;
                         const uint32_t b0_ = b_base + s * C::BTILE;       // plane 0 rows, then plane 1 rows: 2*BN contiguous B rows
+                        if (C::D2X) {
+                            const uint32_t d1 = tmem_d + (uint32_t)(abuf * 2 * BN), d2 = tmem_d + (uint32_t)(BN + tp * 2 * BN);
+                            const bool adjacent = abuf == tp;     // D2 sits right behind this segment's D1
 #pragma unroll
-                        for (int kq = 0; kq < 4; ++kq) {
-                            const uint64_t da0 = interleave_desc(a0 + 2 * kq * LBO, LBO, SBO), da1 = interleave_desc(a1 + 2 * kq * LBO, LBO, SBO);
-                            const uint64_t db = kmajor_desc(b0_ + kq * 32);
-                            mma_bf16(d, da0, db, idesc2, !(seg_start && kq == 0));        // [D1 | D2] += A0 * [B0 ; B1]
-                            mma_bf16(d + BN, da1, db, idesc, 1);                          //       D2  += A1 * B0
+                            for (int kq = 0; kq < 4; ++kq) {
+                                const uint64_t da0 = interleave_desc(a0 + 2 * kq * LBO, LBO, SBO), da1 = interleave_desc(a1 + 2 * kq * LBO, LBO, SBO);
+                                const uint64_t db = kmajor_desc(b0_ + kq * 32), db1 = kmajor_desc(b0_ + BN * 128 + kq * 32);
+                                const bool first_seg = seg_start && kq == 0, first_tile = f == 0 && kq == 0;
+                                if (adjacent && !first_seg) {
+                                    mma_bf16(d1, da0, db, idesc2, 1);                     // [D1 | D2] += A0 * [B0 ; B1]
+                                } else {
+                                    mma_bf16(d1, da0, db, idesc, !first_seg);             // D1 (restarted at a segment start) += A0 * B0
+                                    mma_bf16(d2, da0, db1, idesc, !first_tile);           // D2 (restarted at a tile start)   += A0 * B1
+                                }
+                                mma_bf16(d2, da1, db, idesc, 1);                          // D2 += A1 * B0
+                            }
+                        } else {
+                            const uint32_t d = tmem_d + (uint32_t)(abuf * C::ACC_COLS);
+#pragma unroll
+                            for (int kq = 0; kq < 4; ++kq) {
+                                const uint64_t da0 = interleave_desc(a0 + 2 * kq * LBO, LBO, SBO), da1 = interleave_desc(a1 + 2 * kq * LBO, LBO, SBO);
+                                const uint64_t db = kmajor_desc(b0_ + kq * 32);
+                                mma_bf16(d, da0, db, idesc2, !(seg_start && kq == 0));        // [D1 | D2] += A0 * [B0 ; B1]
+                                mma_bf16(d + BN, da1, db, idesc, 1);                          //       D2  += A1 * B0
+                            }
                         }
                         mma_commit(b_empty(s));
                         if (seg_end) { mma_commit(acc_full(abuf)); ++sg; }
@@ -277,8 +307,8 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
         const int cstart = PRECISE ? (ew >> 2) * COLS : 0;
         const int nflat = p.nkb * taps;
         const int nseg = PRECISE ? (nflat + p.promo_taps - 1) / p.promo_taps : 1;
-        int sg = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int sg = 0, tl = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
             int x0, y0, b0, n0;
             tile_coords(tile, x0, y0, b0, n0);
             const int ex = x0 + (er & 7), ey = y0 + (er >> 3);
@@ -318,27 +348,64 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
                     const int abuf = sg % C::NACC;
                     mbar_wait_t(acc_full(abuf), (sg / C::NACC) & 1, tr, w0);
                     tc_fence_after();
+                    if (C::D2X) {
+                        // D1 only: 4 loads of 16 columns in flight per wait
 #pragma unroll
-                    for (int c = 0; c < COLS / 16; c += G) {
-                        uint32_t v[G][16], v2[G][16];
+                        for (int c = 0; c < COLS / 16; c += 4) {
+                            uint32_t v[4][16];
 #pragma unroll
-                        for (int g = 0; g < G; ++g) {
-                            const uint32_t col = (uint32_t)(abuf * C::ACC_COLS + cstart + (c + g) * 16);
-                            tmem_ld16_async(lane_addr + col, v[g]);
-                            tmem_ld16_async(lane_addr + col + BN, v2[g]);
+                            for (int g = 0; g < 4; ++g) tmem_ld16_async(lane_addr + (uint32_t)(abuf * 2 * BN + cstart + (c + g) * 16), v[g]);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                reg_fence(v[g]);
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) racc[(c + g) * 16 + j] += __uint_as_float(v[g][j]);
+                            }
                         }
-                        tmem_ld_wait();
+                    } else {
 #pragma unroll
-                        for (int g = 0; g < G; ++g) {
-                            reg_fence(v[g]); reg_fence(v2[g]);
+                        for (int c = 0; c < COLS / 16; c += G) {
+                            uint32_t v[G][16], v2[G][16];
 #pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                racc[(c + g) * 16 + j] += fmaf(__uint_as_float(v2[g][j]), 1.f / 2048.f, __uint_as_float(v[g][j]));
+                            for (int g = 0; g < G; ++g) {
+                                const uint32_t col = (uint32_t)(abuf * C::ACC_COLS + cstart + (c + g) * 16);
+                                tmem_ld16_async(lane_addr + col, v[g]);
+                                tmem_ld16_async(lane_addr + col + BN, v2[g]);
+                            }
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int g = 0; g < G; ++g) {
+                                reg_fence(v[g]); reg_fence(v2[g]);
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    racc[(c + g) * 16 + j] += fmaf(__uint_as_float(v2[g][j]), 1.f / 2048.f, __uint_as_float(v[g][j]));
+                            }
                         }
                     }
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acc_empty(abuf));
+                }
+                if (C::D2X) {
+                    // the tile's cross terms, once: the last segment's acc_full also covers every MMA into D2
+                    const int tp = tl & 1;
+#pragma unroll
+                    for (int c = 0; c < COLS / 16; c += 4) {
+                        uint32_t v[4][16];
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) tmem_ld16_async(lane_addr + (uint32_t)(BN + tp * 2 * BN + cstart + (c + g) * 16), v[g]);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            reg_fence(v[g]);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) racc[(c + g) * 16 + j] = fmaf(__uint_as_float(v[g][j]), 1.f / 2048.f, racc[(c + g) * 16 + j]);
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(d2_empty(tp));
                 }
 #pragma unroll
                 for (int j = 0; j < COLS; j += 4) {

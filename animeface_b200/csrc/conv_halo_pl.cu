@@ -231,9 +231,11 @@ static int launch(const CUtensorMap& map, const Params& tp, dim3 grid, cudaStrea
 
 }  // namespace halopl
 
-// ci = channels of the planes input (a multiple of 64: one 128-byte row per pixel), co as conv_halo.cu
+// ci = channels of the planes input: a multiple of 32.  A TMA box always carries 64 channels (one 128-byte row per pixel); for
+// a tensor whose channel count is not a multiple of 64 the box hangs over the channel dimension and TMA fills the overhang
+// with zeros (the packed weight is zero there too), so 32-channel tensors need no padded copy in HBM.
 bool conv_halo_pl_supported(int n, int h, int w, int ci, int co, int k) {
-    if (ci % 64 != 0) return false;
+    if (ci % 32 != 0) return false;
     return conv_halo_supported(n, h, w, ci, co, k);
 }
 
@@ -253,7 +255,7 @@ int conv_fwd_halo_pl(const void* x_planes, const ConvParams& p, cudaStream_t st)
     tp.m_tiles = tp.tiles_x * tp.tiles_y * p.n;
     const int bn = halopl::pick_bn(p.co);
     tp.n_tiles = p.co / bn;
-    tp.nkb = p.ci / 64;
+    tp.nkb = (p.ci + 63) / 64;
     tp.act = p.act; tp.alpha = p.alpha; tp.gain = p.gain;
     dim3 grid((unsigned)std::min(tp.m_tiles * tp.n_tiles, num_sms()));
     if (bn == 128) return halopl::launch<128>(map, tp, grid, st);

@@ -95,19 +95,23 @@ __device__ __forceinline__ float gu_of(const float* gy, const float* y, long lon
     return (y && !(__ldg(y + i) > 0.f)) ? g * slope : g;
 }
 
-// grid (k slices of 128, row groups of 8); 4 warps split n, reduced through shared memory
+// grid (k slices of 32 * KV, row groups of 8); 4 warps split n, reduced through shared memory.  KV = 4 (128-bit weight loads)
+// when K is large enough to fill the machine that way, KV = 1 (more, narrower CTAs) for the 512-wide mapping / affine layers.
+template <int KV>
 __global__ void __launch_bounds__(128) linear_bwd_data_kernel(const float* __restrict__ gy, const float* __restrict__ y, const float* __restrict__ w,
                                                               float* __restrict__ gx, int B, int K, int N, float coef, float gain, float slope) {
-    constexpr int R = 8, NC = 512;
+    constexpr int R = 8, NC = 512, KS = 32 * KV;
     __shared__ float gu[R][NC];
-    __shared__ float red[4][R][128];
+    __shared__ float red[4][R][KS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b0 = blockIdx.y * R, rows = min(R, B - b0);
-    const int k0 = blockIdx.x * 128 + lane * 4;
-    float acc[R][4];
+    const int k0 = blockIdx.x * KS + lane * KV;
+    float acc[R][KV];
 #pragma unroll
-    for (int r = 0; r < R; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f; }
-    const bool vec = (K & 3) == 0 && ((uintptr_t)w & 15) == 0;
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int e = 0; e < KV; ++e) acc[r][e] = 0.f;
+    const bool vec = KV == 4 && (K & 3) == 0 && ((uintptr_t)w & 15) == 0;
     for (int n0 = 0; n0 < N; n0 += NC) {
         const int nn = min(NC, N - n0);
         __syncthreads();
@@ -118,28 +122,30 @@ __global__ void __launch_bounds__(128) linear_bwd_data_kernel(const float* __res
         __syncthreads();
         for (int c = warp; c < nn; c += 4) {
             const float* wr = w + (long long)(n0 + c) * K;
-            float4 wv = f4zero();
-            if (vec) { if (k0 < K) wv = ldg4(wr + k0); }
-            else {
-                wv.x = k0 < K ? __ldg(wr + k0) : 0.f; wv.y = k0 + 1 < K ? __ldg(wr + k0 + 1) : 0.f;
-                wv.z = k0 + 2 < K ? __ldg(wr + k0 + 2) : 0.f; wv.w = k0 + 3 < K ? __ldg(wr + k0 + 3) : 0.f;
+            float wv[KV];
+            if (vec) {
+                const float4 t = k0 < K ? ldg4(wr + k0) : f4zero();
+                wv[0] = t.x; if (KV == 4) { wv[1] = t.y; wv[2] = t.z; wv[3] = t.w; }
+            } else {
+#pragma unroll
+                for (int e = 0; e < KV; ++e) wv[e] = k0 + e < K ? __ldg(wr + k0 + e) : 0.f;
             }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const float g = gu[r][c];
-                acc[r][0] = fmaf(g, wv.x, acc[r][0]); acc[r][1] = fmaf(g, wv.y, acc[r][1]);
-                acc[r][2] = fmaf(g, wv.z, acc[r][2]); acc[r][3] = fmaf(g, wv.w, acc[r][3]);
+#pragma unroll
+                for (int e = 0; e < KV; ++e) acc[r][e] = fmaf(g, wv[e], acc[r][e]);
             }
         }
     }
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) red[warp][r][lane * 4 + e] = acc[r][e];
+        for (int e = 0; e < KV; ++e) red[warp][r][lane * KV + e] = acc[r][e];
     __syncthreads();
-    for (int i = threadIdx.x; i < R * 128; i += 128) {
-        const int r = i / 128, kk = i % 128;
-        const int k = blockIdx.x * 128 + kk;
+    for (int i = threadIdx.x; i < R * KS; i += 128) {
+        const int r = i / KS, kk = i % KS;
+        const int k = blockIdx.x * KS + kk;
         if (r < rows && k < K) gx[(long long)(b0 + r) * K + k] = coef * (red[0][r][kk] + red[1][r][kk] + red[2][r][kk] + red[3][r][kk]);
     }
 }
@@ -208,8 +214,13 @@ extern "C" int sg2_linear_bwd_data(const float* gy, const float* y, const float*
                                    float coef, float gain, float slope, sg2_stream_t stream) {
     SG2_REQUIRE(gy && w && gx, "linear_bwd_data: null pointer");
     SG2_REQUIRE(B > 0 && K > 0 && N > 0, "linear_bwd_data: empty tensor");
-    dim3 grid((unsigned)ceil_div(K, 128), (unsigned)ceil_div(B, 8));
-    lin::linear_bwd_data_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(gy, y, w, gx, B, K, N, coef, gain, slope);
+    if (ceil_div(K, 128) * ceil_div(B, 8) >= num_sms()) {
+        dim3 grid((unsigned)ceil_div(K, 128), (unsigned)ceil_div(B, 8));
+        lin::linear_bwd_data_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>(gy, y, w, gx, B, K, N, coef, gain, slope);
+    } else {
+        dim3 grid((unsigned)ceil_div(K, 32), (unsigned)ceil_div(B, 8));
+        lin::linear_bwd_data_kernel<1><<<grid, 128, 0, (cudaStream_t)stream>>>(gy, y, w, gx, B, K, N, coef, gain, slope);
+    }
     return launched("linear_bwd_data");
 }
 

@@ -197,7 +197,7 @@ static Plan make_plan(int n, int h, int w, int ci, int co, int k) {
     Plan pl{};
     pl.ok = false;
     Params& p = pl.p;
-    if ((k != 1 && k != 3) || ci % 64 != 0 || co % 64 != 0) return pl;
+    if ((k != 1 && k != 3) || ci % 32 != 0 || co % 32 != 0) return pl;      // boxes of 64 channels; TMA zero-fills past the last channel
     if (!pixel_box_ragged(CHUNK, h, w, p.cw, p.ch, p.cb)) return pl;
     if (p.cw < 8) return pl;                                   // an 8-row group of the operands must sit inside one image row
     if ((p.cw + k - 1) * p.ch * p.cb > 40) return pl;
@@ -205,8 +205,8 @@ static Plan make_plan(int n, int h, int w, int ci, int co, int k) {
     p.chunks_x = (w + p.cw - 1) / p.cw; p.chunks_y = (h + p.ch - 1) / p.ch;
     p.total_chunks = p.chunks_x * p.chunks_y * ((n + p.cb - 1) / p.cb);
     p.stack = (co % 128 != 0) ? 1 : 0;
-    p.co_tiles = co / (p.stack ? 64 : 128);
-    p.ci_tiles = ci / 64;
+    p.co_tiles = (co + (p.stack ? 63 : 127)) / (p.stack ? 64 : 128);
+    p.ci_tiles = (ci + 63) / 64;
     p.ncols = 64 * k;
     pl.tiles = p.co_tiles * p.ci_tiles * k;
     int splits = std::max(1, (2 * num_sms()) / pl.tiles);

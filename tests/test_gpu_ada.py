@@ -82,6 +82,7 @@ def test_second_order_through_the_pipeline(g_ada):
     av, = torch.autograd.grad(gx, gy, v)
     with rng.replay(draws()):
         y0 = pipe(torch.zeros_like(x))                      # the affine offset (brightness)
+    with rng.replay(draws()):
         yv = pipe(v)
     assert rel_err(N(av), N(yv - y0)) < 1e-4
 

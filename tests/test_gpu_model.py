@@ -239,8 +239,9 @@ def test_amp_mode_step_matches_fp32_step(g_model):
     """The reference's DEFAULT run mode (MiniAccelerator(amp=True): fp16 autocast + GradScaler, implementations/StyleGAN2/
     utils.py:47,62-113,167) on this package: autocast regions, scaler.scale(loss).backward(), the scaler-aware R1
     ``calc_grad`` (nnutils/loss/penalty.py:11-26) and optimizer.step() through the scaler.  The kernels compute and store
-    fp32 under autocast, so two steps (the second an R1 step) must land on the amp=False weights up to the scaler's
-    scale / unscale rounding."""
+    fp32 under autocast; what autocast still turns into half precision is the torch-side glue between them (the
+    demodulation matmul, loss arithmetic), so two steps (the second an R1 step) land on the amp=False run to AMP's own
+    precision -- 2e-3, against fp16's 1e-3 unit round-off -- not to fp32 round-off."""
     from animeface_b200 import rng
     from animeface_b200.diffaugment import DiffAugment
     from animeface_b200.nnutils import MiniAccelerator, update_ema
@@ -294,8 +295,8 @@ def test_amp_mode_step_matches_fp32_step(g_model):
     la, ga, da = run(True)
     lf, gf, df = run(False)
     for (d1, g1), (d2, g2) in zip(la, lf):
-        assert abs(d1 - d2) < 1e-4 * abs(d2) and abs(g1 - g2) < 1e-4 * abs(g2), (la, lf)
-    assert rel_err(N(ga), N(gf)) < 1e-4 and rel_err(N(da), N(df)) < 1e-4, (rel_err(N(ga), N(gf)), rel_err(N(da), N(df)))
+        assert abs(d1 - d2) < 2e-3 * abs(d2) and abs(g1 - g2) < 2e-3 * abs(g2), (la, lf)
+    assert rel_err(N(ga), N(gf)) < 2e-3 and rel_err(N(da), N(df)) < 2e-3, (rel_err(N(ga), N(gf)), rel_err(N(da), N(df)))
     # and the fp32 run is the reference's trajectory (steps 1 and 2 from the reference's step-1 weights are not in the golden;
     # the losses of a fresh start are): sanity that the loop above is the reference's loop
     assert all(np.isfinite(v) for pair in la + lf for v in pair)

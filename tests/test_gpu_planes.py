@@ -67,6 +67,7 @@ def test_bwd_prep_planes_matches_torch_and_is_deterministic(slope, with_d):
 CONV_CASES = [  # n, cin (planes), cout, k, h, w
     (2, 64, 64, 3, 16, 16), (2, 64, 32, 3, 32, 32), (3, 128, 64, 3, 16, 32), (2, 64, 128, 1, 16, 16), (1, 256, 256, 3, 16, 16),
     (2, 64, 64, 3, 40, 33), (4, 512, 512, 3, 8, 8), (2, 128, 128, 3, 64, 64), (1, 64, 64, 1, 32, 48),
+    (2, 32, 64, 3, 32, 32), (2, 32, 32, 3, 64, 64), (2, 96, 32, 3, 16, 16), (2, 32, 64, 1, 16, 16),
 ]
 
 
@@ -91,6 +92,7 @@ def test_data_gradient_conv_on_planes(n, cin, cout, k, h, w):
 WGRAD_CASES = [  # n, ci, co, k, h, w
     (2, 64, 64, 3, 16, 16), (2, 64, 128, 3, 32, 32), (3, 128, 64, 3, 8, 8), (2, 64, 192, 1, 16, 16), (1, 256, 256, 3, 16, 16),
     (2, 64, 64, 3, 40, 33), (4, 128, 512, 3, 8, 16), (2, 64, 64, 3, 64, 64), (2, 128, 128, 1, 32, 32), (5, 64, 64, 3, 8, 8),
+    (2, 32, 64, 3, 32, 32), (2, 64, 32, 3, 32, 32), (2, 32, 32, 3, 64, 64), (2, 32, 64, 1, 16, 16), (2, 96, 160, 3, 16, 16),
 ]
 
 
