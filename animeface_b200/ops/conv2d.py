@@ -415,11 +415,20 @@ class ModConvFn(torch.autograd.Function):
                 float(ctx.slope if ctx.slope is not None else 1.0), ws.data_ptr(), st), 'sg2_modconv_bwd_prep')
             gb = gb_part.sum(0)
         else:
-            # few output channels (ToRGB, Co=3): the tensors are tiny, keep this prologue in torch.
-            assert ctx.slope is None and d is None
-            g_acc = gy
-            gb = gy.sum((0, 2, 3))
+            # output channel counts the vectorised prologue does not take (ToRGB's Co = 3: tiny tensors; the odd widths of
+            # the StyleGAN3 generator): the same arithmetic as sg2_modconv_bwd_prep in tensor ops
+            gu = gy if ctx.slope is None else gy * torch.where(y > 0, 1.0, float(ctx.slope))
+            gb = gu.sum((0, 2, 3))
             gd = None
+            if d is not None:
+                u = y if ctx.slope is None else torch.where(y > 0, y, y / float(ctx.slope))
+                if b is not None:
+                    u = u - b.reshape(1, -1, 1, 1)
+                if noise is not None:
+                    u = u - noise
+                gd = (gu * u).sum((2, 3)) / d
+                gu = gu * d[:, :, None, None]
+            g_acc = gu
         gx = gw = gs = None
         # data gradient w.r.t. the modulated input, then gs = sum_hw g_xs * x and gx = g_xs * s in one pass
         g_xs = _conv_planes(g_acc_p, w, ctx.coef, True) if use_planes else _conv_raw(g_acc, w, ctx.coef, True)
@@ -476,7 +485,7 @@ def _modulated_conv2d_any_order(x, w, s, d, bias, noise, coef, slope):
     return acc
 
 
-def modulated_conv2d(x, w, s, bias=None, noise=None, demod=True, slope=None, eps=1e-4, out_nchw=False):
+def modulated_conv2d(x, w, s, bias=None, noise=None, demod=True, slope=None, eps=1e-4, out_nchw=False, in_gain=None):
     """ModulatedConv2d.forward (model.py:106-132) (+ InjectNoise :85-88 + LeakyReLU :164 when given).
 
     x [B,Ci,H,W]; w [Co,Ci,k,k]; s [B,Ci] = affine(style) + 1 (model.py:110); bias [1,Co,1,1];
@@ -488,6 +497,10 @@ def modulated_conv2d(x, w, s, bias=None, noise=None, demod=True, slope=None, eps
     if demod:
         wsq = w.square().sum((2, 3))                       # [Co,Ci]
         d = torch.rsqrt(torch.matmul(s.square(), wsq.t()) * (coef * coef) + eps)
+    if in_gain is not None:
+        # StyleGAN3's magnitude-EMA input gain (implementations/StyleGAN3/model.py:62-65): scales the weight per input channel
+        # AFTER demodulation, i.e. it rides with the style on the activation tile but stays out of d
+        s = s * in_gain
     if _any_order:
         return _modulated_conv2d_any_order(x, w, s, d, bias, noise, coef, slope)
     return ModConvFn.apply(x, w, s, d, bias, noise, coef, slope, out_nchw)

@@ -71,6 +71,9 @@ class TrainConfig:
     pl_lambda: float = 0.
     policy: str = 'color,translation'
     ema_decay: float = 0.999
+    # 'diffaugment' = the StyleGAN2 loop's DiffAugment(policy) (utils.py:63-68); 'ada' = BASELINE config 4: nnutils.ada.ADA(batch_size)
+    # in its place, its strength p following sign(D(real)) (nnutils/ada.py:25-36; implementations/ADA/utils.py:70)
+    augment: str = 'diffaugment'
 
 
 def build_models(cfg: TrainConfig, device):
@@ -123,7 +126,14 @@ class Trainer:
         self.cfg, self.G, self.G_ema, self.D, self.opt_g, self.opt_d = cfg, G, G_ema, D, opt_g, opt_d
         self.loss = NonSaturatingLoss()
         self.r1 = r1_regularizer()
-        self.augment = functools.partial(DiffAugment, policy=cfg.policy)
+        if cfg.augment == 'ada':
+            from .ada import ADA
+            self.ada = ADA(batch_size=cfg.batch_size).to(next(G.parameters()).device)
+            self.augment = self.ada
+        else:
+            assert cfg.augment == 'diffaugment', cfg.augment
+            self.ada = None
+            self.augment = functools.partial(DiffAugment, policy=cfg.policy)
         self.batches_done = 0
         self._d_params = list(D.parameters())
         # running mean of the path-length penalty (utils.py:44, 100-103), on the device so the step never syncs
@@ -162,6 +172,8 @@ class Trainer:
             with independent_batches(2):
                 prob = D(torch.cat([real_aug, fake_aug], dim=0))
             D_loss = self.loss.d_loss(prob[:B], prob[B:])
+            if self.ada is not None:
+                self.ada.update_p(prob[:B].detach())          # overfitting heuristic on D(real_aug); device-side, no sync
         D_loss.backward()
         self.opt_d.step()
         # ---- generator phase (utils.py:88-113)

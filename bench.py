@@ -105,23 +105,40 @@ def cpu_oracle_step_rate(batch, steps, warmup, threads=None):
     return batch * steps / total, total / steps, torch.get_num_threads()
 
 
+def workload_config(args):
+    """The `config` both arms print: BASELINE config 2 (the metric's configuration) or, with --config 4, config 4."""
+    if args.config == 4:
+        return dict(workload='BASELINE config 4: StyleGAN2 512x512 (channels=32, max 512, style_dim 512) + ADA augment pipeline '
+                             '(nnutils.ada.ADA in place of DiffAugment), batch 16 per GPU, R1 every 16 steps, Adam, EMA; fp32 storage',
+                    batch_per_gpu=args.batch, image_size=512)
+    return dict(workload='BASELINE config 2: StyleGAN2 256x256 (channels=32, max 512, style_dim 512), batch 32 per GPU, '
+                         'R1 every 16 steps, DiffAugment color,translation, Adam, EMA; fp32 storage',
+                batch_per_gpu=args.batch, image_size=256)
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    batch = 4 if args.steps + args.warmup <= 30 else 2
+    # the reference's step on the host cores costs ~0.4 s per image: a step of the full batch (32) when the run is short
+    # enough to end within a few minutes, else a bounded sample of it (stated in `sample`)
+    total = args.steps + args.warmup
+    batch = args.batch if total <= 6 else (16 if total <= 12 else (8 if total <= 26 else 4))
+    batch = min(batch, args.batch)
     # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers: override it)
     try:
         threads = len(os.sched_getaffinity(0))
     except AttributeError:
         threads = os.cpu_count() or 1
     ips, sec, cores = cpu_oracle_step_rate(batch, args.steps, args.warmup, threads=threads)
-    sample = f'oracle port (oracle/sg2_torch.py, plain PyTorch fp32 CPU) of the same step at B={batch} per step, {args.steps} timed steps'
+    sample = (f'oracle port (oracle/sg2_torch.py, plain PyTorch fp32 CPU) of the same step at B={batch} per step '
+              f'({"the full batch" if batch == args.batch else "a bounded sample of the batch of " + str(args.batch)}), {args.steps} timed steps')
+    cfg = workload_config(args)
+    cfg['sample_batch'] = batch
     line = dict(impl='reference', metric='StyleGAN2 256px G+D step images/sec', value=round(ips, 4), unit='images/sec',
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=round(sec * 1e3, 1),
                 higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
-                config=dict(workload='StyleGAN2 256x256 config of implementations/StyleGAN2 (channels=32, style_dim=512), '
-                                     'R1 every 16 steps, DiffAugment color,translation; CPU sample', batch_per_step=batch),
+                config=cfg,
                 cpu_baseline=dict(value=round(ips, 4), unit='images/sec', cores=cores, kind='port', sample=sample),
                 e2e=dict(value=round(ips, 4), unit='images/sec', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)

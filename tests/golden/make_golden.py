@@ -12,6 +12,7 @@ that the oracle and the GPU path can replay them.  Files (all small, committed):
     model.npz    small G/D: images, logits, losses, all parameter gradients, R1, 3-step trajectory
     sg3d.npz     StyleGAN3-style discriminator (implementations/StyleGAN3/model.py:382-510): logits, D-loss and R1
                  parameter gradients, conv2d_resample cases
+    sg3g.npz     StyleGAN3 generator (implementations/StyleGAN3/model.py:32-380) and filtered_lrelu cases incl. gradients
     ada.npz      AugmentPipe / ADA (thirdparty/ada/augment.py, nnutils/ada.py): outputs, gradients, recorded draws, p updates
     resample.npz conv2d_resample up-sampling / grouped branches and conv_transpose2d incl. gradients
     pl.npz       path-length penalty (implementations/StyleGAN2/utils.py:18-33): value, per-sample gradient norms,
@@ -473,6 +474,59 @@ def gen_ada():
     print('ada.npz', len(out))
 
 
+def gen_sg3g():
+    """StyleGAN3 generator (implementations/StyleGAN3/model.py:32-380) and filtered_lrelu (thirdparty/stylegan3_ops/ops/
+    filtered_lrelu.py, reference path) through the reference's own code (CPU, fp32): image, updated EMA buffers, all parameter
+    gradients; stand-alone filtered_lrelu cases incl. gradients."""
+    from implementations.StyleGAN3 import model as sg3
+    from thirdparty.stylegan3_ops.ops import filtered_lrelu as ref_fl
+    out = {}
+    torch.manual_seed(4711)
+    cfg = dict(image_size=32, latent_dim=32, num_layers=6, map_num_layers=2, channels=16, max_channels=32, style_dim=32)
+    out['cfg'] = np.array(repr(cfg))
+    G = sg3.Generator(**cfg)
+    for p_ in G.parameters():                       # biases start at 0 / 1: move them so their gradients are exercised
+        if p_.ndim == 1:
+            p_.data.add_(torch.randn_like(p_) * 0.1)
+    for k, v in G.state_dict().items():
+        out['G0.' + k] = A(v)
+    z = torch.randn(3, 32)
+    out['z'] = A(z)
+    G.train()
+    img = G(z)
+    gy = torch.randn_like(img)
+    out['image'] = A(img); out['gy'] = A(gy)
+    grads = torch.autograd.grad(img, list(G.parameters()), gy, allow_unused=True)
+    for (n_, p_), g_ in zip(G.named_parameters(), grads):
+        out['grad.' + n_] = A(g_) if g_ is not None else np.zeros(p_.shape, np.float32)
+    for k, v in G.state_dict().items():             # buffers after one training-mode forward (magnitude EMAs, w_avg)
+        if 'ema' in k or 'w_avg' in k:
+            out['G1.' + k] = A(v)
+    G.eval()
+    out['image_eval_psi07'] = A(G(z, truncation_psi=0.7))
+    # filtered_lrelu cases: (name, channels, hw, up, down, fu taps, fd (taps | 'radial'), padding, gain, slope, clamp)
+    cases = [('u2d2', 4, 10, 2, 2, 12, 12, [9, 8, 9, 8], 2 ** 0.5, 0.2, 256), ('u4d2', 3, 16, 4, 2, 24, 12, [-6, -9, -6, -9], 2 ** 0.5, 0.2, 256),
+             ('u2d2r', 4, 10, 2, 2, 12, 'radial', [9, 8, 9, 8], 2 ** 0.5, 0.2, 1.5), ('u1d1', 5, 8, 1, 1, 1, 1, 0, 1.0, 1.0, None),
+             ('u2d1', 3, 8, 2, 1, 8, 1, [3, 4, 3, 4], 1.3, 0.1, None)]
+    out['fl.cases'] = np.array([repr(c) for c in cases])
+    for name, ch, hw, up, down, fu_t, fd_t, pad, gain, slope, clamp in cases:
+        fu = sg3.design_filter(fu_t, 2.0, 2.0, 16.0) if fu_t > 1 else None
+        fd = (sg3.design_filter(12, 2.0, 2.0, 16.0, radial=True) if fd_t == 'radial' else (sg3.design_filter(fd_t, 2.0, 2.0, 16.0) if fd_t > 1 else None))
+        x = torch.randn(2, ch, hw, hw + 3, requires_grad=True)
+        b = torch.randn(ch, requires_grad=True)
+        y = ref_fl.filtered_lrelu(x, fu, fd, b, up, down, pad, gain, slope, clamp, impl='ref')
+        g_ = torch.randn_like(y)
+        gx, gb = torch.autograd.grad(y, (x, b), g_)
+        for key, t in (('x', x), ('b', b), ('y', y), ('gy', g_), ('gx', gx), ('gb', gb)):
+            out[f'fl.{name}.{key}'] = A(t)
+        if fu is not None:
+            out[f'fl.{name}.fu'] = A(fu)
+        if fd is not None:
+            out[f'fl.{name}.fd'] = A(fd)
+    np.savez_compressed(os.path.join(HERE, 'sg3g.npz'), **out)
+    print('sg3g.npz', len(out))
+
+
 def gen_resample():
     """conv2d_resample up-sampling / grouped branches and conv2d_gradfix.conv_transpose2d through the reference's own code
     (thirdparty/stylegan3_ops/ops/conv2d_resample.py:40-141, conv2d_gradfix.py:29-46; CPU, fp32), incl. gradients."""
@@ -520,7 +574,7 @@ def gen_resample():
 if __name__ == '__main__':
     if len(sys.argv) > 1:                                         # regenerate only the named files
         for name in sys.argv[1:]:
-            dict(ops=gen_ops, modules=gen_modules, model=gen_model, pl=gen_pl, sg3d=gen_sg3d, resample=gen_resample, ada=gen_ada)[name]()
+            dict(ops=gen_ops, modules=gen_modules, model=gen_model, pl=gen_pl, sg3d=gen_sg3d, resample=gen_resample, ada=gen_ada, sg3g=gen_sg3g)[name]()
         sys.exit(0)
     gen_ops()
     gen_modules()
@@ -529,5 +583,6 @@ if __name__ == '__main__':
     gen_sg3d()
     gen_resample()
     gen_ada()
-    for f in ('ops.npz', 'modules.npz', 'model.npz', 'pl.npz', 'sg3d.npz', 'resample.npz', 'ada.npz'):
+    gen_sg3g()
+    for f in ('ops.npz', 'modules.npz', 'model.npz', 'pl.npz', 'sg3d.npz', 'resample.npz', 'ada.npz', 'sg3g.npz'):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, 'KiB')

@@ -247,3 +247,22 @@ def test_oracle_conv2d_resample_up_and_grouped_cases(g_resample):
         x, w, b = (torch.from_numpy(g[f'ct.{name}.{t}']) for t in 'xwb')
         y = S.conv_transpose2d(x, w, b, stride, pad, opad, groups)
         assert rel_err(y.numpy(), g[f'ct.{name}.y']) < 1e-6, name
+
+
+def test_oracle_filtered_lrelu_cases():
+    """oracle/sg3g_torch.py against the reference's filtered_lrelu incl. gradients (tests/golden/sg3g.npz)."""
+    import ast
+    import torch
+    from conftest import Golden
+    from oracle import sg3g_torch as S
+    g = Golden('sg3g.npz')
+    for case in [ast.literal_eval(str(c)) for c in g['fl.cases']]:
+        name, ch, hw, up, down, fu_t, fd_t, pad, gain, slope, clamp = case
+        fu = torch.from_numpy(g[f'fl.{name}.fu']) if f'fl.{name}.fu' in g else None
+        fd = torch.from_numpy(g[f'fl.{name}.fd']) if f'fl.{name}.fd' in g else None
+        x = torch.from_numpy(g[f'fl.{name}.x']).requires_grad_(True)
+        b = torch.from_numpy(g[f'fl.{name}.b']).requires_grad_(True)
+        y = S.filtered_lrelu(x, fu, fd, b, up, down, pad, gain, slope, clamp)
+        assert rel_err(y.detach().numpy(), g[f'fl.{name}.y']) < 2e-6, name
+        gx, gb = torch.autograd.grad(y, (x, b), torch.from_numpy(g[f'fl.{name}.gy']))
+        assert rel_err(gx.numpy(), g[f'fl.{name}.gx']) < 2e-6 and rel_err(gb.numpy(), g[f'fl.{name}.gb']) < 2e-6, name
