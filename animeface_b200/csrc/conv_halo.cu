@@ -566,17 +566,17 @@ int conv_fwd_halo(const ConvParams& p, int precise, cudaStream_t st) {
     tp.trace = g_trace;
     // promotion interval of the fp32-class kernel (taps accumulated in TMEM between two promotions, 4 chained big*big MMAs
     // each).  Error of one convolution against fp64 (scripts/promo_sweep.py, profiles/r1b_promo_sweep.txt): 2 taps 3.5e-7,
-    // 5 taps 5e-7, 9 taps (one promotion per 64-channel block) 0.8..1.1e-6 -- torch/cuDNN fp32 itself is 0.3..2e-6 on the same
-    // cases.  At full model width and batch 32 (tests/test_gpu_fullwidth.py, profiles/r2h_promo_sweep.txt) every interval keeps
-    // every gradient class inside the reference's own fp32 noise (two cuDNN evaluations of the reference differ from fp64 by
-    // 1.7e-2 on the R1 bias gradients, 1.8e-3 on G weight gradients), and the generated image stays 7x closer to fp64 than
-    // the reference's fp32 (7e-6 vs 5e-5) even at 9 taps: round 1's choice of 2 read per-tensor noise as a trend.  Default 9:
-    // 10..16 % faster forward convolutions.  SG2_PROMO_TAPS overrides it for the sweep.
+    // 5 taps 5e-7, 9 taps 0.8..1.1e-6 -- torch/cuDNN fp32 itself is 0.3..2e-6 on the same cases.  What decides the setting is the
+    // full-width model (scripts/noise_study.py, profiles/r2j_noise_study.txt: 3 seeds, every gradient class, ours and four fp32
+    // evaluations of the reference against fp64): at 2 taps ours is 3-5x CLOSER to fp64 than the reference's own fp32 arithmetic
+    // (median over a class), at 5 taps on par or better in every class (G gradients 7e-5 vs 8e-5, D gradients 3e-5 vs 5e-5, R1
+    // bias gradients 8e-4 vs 1.2e-3), at 9 taps 1.2-4x worse.  Default 5: never less accurate than the reference, 6-9 % faster
+    // forward convolutions than 2.  SG2_PROMO_TAPS overrides it for the sweeps.
     static int promo_taps = 0;
     if (!promo_taps) {
         const char* e = getenv("SG2_PROMO_TAPS");
-        promo_taps = e ? atoi(e) : 9;
-        if (promo_taps < 1 || promo_taps > 9) promo_taps = 9;
+        promo_taps = e ? atoi(e) : 5;
+        if (promo_taps < 1 || promo_taps > 9) promo_taps = 5;
     }
     tp.promo_taps = promo_taps;
     dim3 grid((unsigned)std::min(tp.m_tiles * tp.n_tiles, num_sms()));

@@ -301,7 +301,7 @@ static int launch_ring_cols(const UpfirdnParams& p, cudaStream_t st) {
     constexpr int STRIP = 16;       // 32 halves the halo re-read but leaves the 257-row images of U4 with a nearly empty 9th strip: slower
     constexpr bool NHWC = sizeof(V) == 16;
     dim3 grid;
-    if (NHWC) grid = dim3((unsigned)ceil_div(p.out_w, 256 / (p.c / 4)), (unsigned)ceil_div(p.out_h, STRIP), (unsigned)p.n);
+    if (NHWC) grid = dim3((unsigned)ceil_div(ceil_div(p.out_w, COLS), 256 / (p.c / 4)), (unsigned)ceil_div(p.out_h, STRIP), (unsigned)p.n);
     else grid = dim3((unsigned)ceil_div(ceil_div(p.out_w, COLS) * ceil_div(p.out_h, STRIP), 256), 1u, (unsigned)(p.n * p.c));
     upfirdn2d_ring_kernel<V, FH, FW, DOWN, COLS, STRIP><<<grid, 256, 0, st>>>(p);
     return launched("upfirdn2d_ring");
@@ -311,6 +311,14 @@ template <class V, int FH, int FW, int DOWN>
 static int launch_ring(const UpfirdnParams& p, cudaStream_t st) {
     // NHWC: a thread = one pixel column x 4 channels.  NCHW: COLS adjacent columns of one plane.
     if constexpr (sizeof(V) == 16) {
+        // adjacent pixels per thread: with 1 every input pixel is fetched FW times through L1 (4 x the data for the 4x4 blur:
+        // ~92 B/clk/SM of L1 traffic at HBM speed, next to the 128 B/clk the L1 delivers); 2 pixels share a 5-wide window
+        // (2.5 x).  SG2_UPF_COLS_NHWC overrides the choice for the sweep (profiles/r2k_upfirdn_cols.txt).
+        static int cols = 0;
+        if (!cols) { const char* e = getenv("SG2_UPF_COLS_NHWC"); cols = e ? atoi(e) : -1; }
+        const int use = cols > 0 ? cols : (DOWN == 1 ? 2 : 1);
+        if (use == 4) return launch_ring_cols<V, FH, FW, DOWN, 4>(p, st);
+        if (use == 2) return launch_ring_cols<V, FH, FW, DOWN, 2>(p, st);
         return launch_ring_cols<V, FH, FW, DOWN, 1>(p, st);
     } else {
         // columns per thread, measured on B200 (U4, NCHW, fraction of HBM peak): filter 1 -> 0.35, 2 -> 0.48, 4 -> 0.56;

@@ -23,7 +23,15 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FLOP_PER_IMG_STEP = 370.7e9          # D phase 217.7 + G phase 152.9 GFLOP per image, normal step
+
+
+def load_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/r2_ncu_traffic.json,
+    written by scripts/ncu_summary.py from the .ncu-rep of the same shapes); None when the file is absent."""
+    try:
+        return json.load(open(os.path.join(ROOT, 'profiles', 'r2_ncu_traffic.json')))
+    except Exception:
+        return None
 
 
 def load_peaks():
@@ -208,7 +216,10 @@ def run_b200(args):
         init_distributed('nccl')
     peaks = load_peaks()
     B = args.batch
-    cfg = TrainConfig(batch_size=B)
+    size = 512 if args.config == 4 else 256
+    cfg = TrainConfig(batch_size=B, image_size=size, augment='ada' if args.config == 4 else 'diffaugment')
+    if args.config == 4:
+        args.graphs = False        # the ADA geometry reads its data-dependent padding back to the host (augment.py:281): no capture
     torch.manual_seed(0)                                 # identical replicas (weights), rank-distinct data below
     G, G_ema, D = build_models(cfg, dev)
     opt_g, opt_d = build_optimizers(cfg, G, G_ema, D)
@@ -222,7 +233,7 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     # resident synthetic batches (uniform [-1,1] like T.Normalize(0.5,0.5) output), a few so steps differ
-    pool = [torch.rand(B, 3, 256, 256, device=dev) * 2 - 1 for _ in range(4)]
+    pool = [torch.rand(B, 3, size, size, device=dev) * 2 - 1 for _ in range(4)]
     if args.graphs:
         tr.prime(pool[0])                                 # eager + capture of both step kinds (4 untimed steps)
         eager.batches_done = 0
@@ -248,6 +259,8 @@ def run_b200(args):
     launches = _lib.launch_count() - launches0
     conv_log, C.launch_log = C.launch_log, None
     roofline_note = 'timed region'
+    if args.config == 4 and eager.ada is not None:
+        eager.ada.p.fill_(0.5)     # a mid-training augmentation strength (p starts at 0 = identity transforms)
     if args.graphs:
         # graph replays bypass the host-side launch counter and the per-launch events: measure both in a separate
         # eager pass over the same K steps (same schedule position), AFTER the timed region
@@ -279,7 +292,7 @@ def run_b200(args):
         d = by_kind.setdefault(kind, [0.0, 0.0, 0])
         d[0] += f; d[1] += a.elapsed_time(b); d[2] += 1
     roofline = dict(bound='tensor', achieved=round(achieved, 2), peak=peaks['tf'], unit='TFLOP/s',
-                    frac=round(achieved / peaks['tf'], 4), traffic=None,
+                    frac=round(achieved / peaks['tf'], 4), traffic=load_traffic(),
                     kernel='conv2d fwd/dgrad/wgrad (all launches of K steps)', measured_in=roofline_note,
                     peak_source=f"bf16_tflops_sustained of MEASURED_PEAKS.json ({peaks['src']})",
                     share_of_step=round(conv_ms / max(ms, 1e-9), 3),
@@ -292,7 +305,7 @@ def run_b200(args):
                          'and DRAM bytes per launch: profiles/r1d_ncu_full_conv_wgrad.txt')
 
     # ---- end-to-end: host batch in pinned memory -> H2D each step, losses read back each step
-    host = [torch.empty(B, 3, 256, 256, pin_memory=True).uniform_(-1, 1) for _ in range(2)]
+    host = [torch.empty(B, 3, size, size, pin_memory=True).uniform_(-1, 1) for _ in range(2)]
     sync()
     e0.record()
     for i in range(args.steps):
@@ -306,7 +319,7 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t)
     e2e = dict(value=round(world * B * args.steps / (e2e_ms / 1e3), 2), unit='images/sec',
-               h2d_bytes_per_step=B * 3 * 256 * 256 * 4, d2h_bytes_per_step=8)
+               h2d_bytes_per_step=B * 3 * size * size * 4, d2h_bytes_per_step=8)
 
     def finish():
         # Every rank leaves through here.  The CUDA graphs hold captured NCCL work, and tearing the process group down
@@ -322,22 +335,23 @@ def run_b200(args):
         finish()
         return
     # second half of BASELINE.json's metric: upfirdn2d achieved HBM GB/s on the SURVEY 8(d) inputs (rank 0, N = 1 only)
-    upf = upfirdn2d_rates(dev, peaks) if world == 1 else None
+    upf = upfirdn2d_rates(dev, peaks) if (world == 1 and args.config == 2) else None
     cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
-        ips, sec, cores = cpu_oracle_step_rate(4, 2, 1, threads=(len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else None))
+    if world == 1 and not args.no_cpu_baseline and args.config == 2:
+        ips, sec, cores = cpu_oracle_step_rate(8, 2, 1, threads=(len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else None))
         cpu_baseline = dict(value=round(ips, 4), unit='images/sec', cores=cores, kind='port',
-                            sample='oracle/sg2_torch.py (plain-PyTorch CPU restatement of the reference step) at B=4: '
+                            sample='oracle/sg2_torch.py (plain-PyTorch CPU restatement of the reference step) on a bounded sample, B=8 of the 32: '
                                    f'1 warm-up + 2 timed steps, {sec:.1f} s/step')
-    line = dict(metric='StyleGAN2 256px G+D step images/sec', value=round(value, 2), unit='images/sec', n_gpus=world,
+    wcfg = workload_config(args)
+    executed_gflop_per_img = conv_flops / (args.steps * B) / 1e9       # convolution flops the step really executes, per image
+    wcfg.update(parallelism=f'dp{world}', conv_impl=args.conv_impl, cuda_graphs=bool(args.graphs),
+                l2='per-step working set (activations, several GB) >> 126 MB L2; no explicit flush',
+                r1_steps_in_timed_region=sum(1 for i in range(args.steps) if (args.warmup + i) % cfg.d_k == 0 and (args.warmup + i) != 0),
+                executed_conv_gflop_per_image=round(executed_gflop_per_img, 1),
+                model_tflops=round(value * executed_gflop_per_img / 1e3, 2))
+    line = dict(metric=f'StyleGAN2 {size}px G+D step images/sec', value=round(value, 2), unit='images/sec', n_gpus=world,
                 steps=args.steps, warmup=args.warmup, ms_per_step=round(ms / args.steps, 3), higher_is_better=True,
-                scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
-                config=dict(workload='BASELINE config 2: StyleGAN2 256x256 (channels=32, max 512, style_dim 512), batch 32 per GPU, '
-                                     'R1 every 16 steps, DiffAugment color,translation, Adam, EMA; fp32 storage',
-                            batch_per_gpu=B, parallelism=f'dp{world}', conv_impl=args.conv_impl, cuda_graphs=bool(args.graphs),
-                            l2='per-step working set (activations, several GB) >> 126 MB L2; no explicit flush',
-                            r1_steps_in_timed_region=sum(1 for i in range(args.steps) if (args.warmup + i) % cfg.d_k == 0 and (args.warmup + i) != 0),
-                            model_tflops=round(value * FLOP_PER_IMG_STEP / 1e12, 2)),
+                scaling='weak', vs_baseline=None, dtype='f32', data='synthetic', config=wcfg,
                 clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu_baseline,
                 upfirdn2d=upf)
     if json_fd is not None:
@@ -353,11 +367,14 @@ def main():
     ap.add_argument('--steps', type=int, default=16)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--batch', type=int, default=32, help='per-GPU batch (BASELINE config 2/3: 32)')
+    ap.add_argument('--config', type=int, default=2, choices=[2, 4], help='BASELINE config: 2 (256 px, the metric) or 4 (512 px + ADA)')
+    ap.add_argument('--batch', type=int, default=None, help='per-GPU batch (BASELINE config 2/3: 32, config 4: 16)')
     ap.add_argument('--conv-impl', default='auto', choices=['auto', 'simt', 'tc'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graphs', dest='graphs', action='store_false', help='run the step eagerly instead of replaying CUDA graphs')
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = 16 if args.config == 4 else 32
     if args.impl == 'reference':
         run_reference(args)
         return
