@@ -50,9 +50,9 @@ SIGNATURES = {
     'sg2_modconv_bwd_prep': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _f, _vp, _vp]),
     'sg2_split_planes': (_int, [_vp, _vp, _vp, _int, _int, _int, _vp]),
     'sg2_bwd_prep_planes_workspace': (_i64, [_int, _int, _int]),
-    'sg2_bwd_prep_planes': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _f, _vp]),
+    'sg2_bwd_prep_planes': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _f, _int, _f, _vp]),
     'sg2_conv2d_planes_supported': (_int, [_int, _int, _int, _int, _int, _int, _int]),
-    'sg2_conv2d_fwd_planes': (_int, [_vp, _vp, _vp, _i64p, _int, _int, _int, _int, _int, _int, _vp, _vp, _int, _f, _f, _vp]),
+    'sg2_conv2d_fwd_planes': (_int, [_vp, _vp, _vp, _i64p, _int, _int, _int, _int, _int, _int, _vp, _vp, _int, _f, _f, _int, _vp]),
     'sg2_conv2d_wgrad_planes_workspace': (_i64, [_int, _int, _int, _int, _int, _int]),
     'sg2_conv2d_wgrad_planes': (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _f, _int, _vp]),
     'sg2_linear_fwd': (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _f, _f, _f, _vp]),

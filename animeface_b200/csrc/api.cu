@@ -147,7 +147,7 @@ extern "C" int sg2_conv2d_planes_supported(int n, int h, int w, int ci, int co, 
 extern "C" int sg2_conv2d_fwd_planes(const void* x_planes, const void* packed_w, float* y, const int64_t y_strides[4],
                                      int n, int h, int w, int ci, int co, int k,
                                      const float* out_scale, const float* bias, int act, float alpha, float gain,
-                                     sg2_stream_t stream) {
+                                     int accumulate, sg2_stream_t stream) {
     SG2_REQUIRE(x_planes && packed_w && y, "conv2d_fwd_planes: null pointer");
     SG2_REQUIRE(n > 0 && h > 0 && w > 0 && ci > 0 && co > 0, "conv2d_fwd_planes: empty tensor");
     SG2_REQUIRE(k == 1 || k == 3, "conv2d_fwd_planes: kernel size %d not supported (1 or 3)", k);
@@ -159,7 +159,7 @@ extern "C" int sg2_conv2d_fwd_planes(const void* x_planes, const void* packed_w,
     p.n = n; p.h = h; p.w = w; p.ci = ci; p.co = co; p.k = k;
     p.in_scale = nullptr; p.out_scale = out_scale; p.bias = bias; p.noise = nullptr;
     p.act = act; p.alpha = alpha; p.gain = gain;
-    return conv_fwd_halo_pl(x_planes, p, (cudaStream_t)stream);
+    return conv_fwd_halo_pl(x_planes, p, accumulate, (cudaStream_t)stream);
 }
 
 extern "C" int64_t sg2_conv2d_wgrad_planes_workspace(int n, int h, int w, int ci, int co, int k) {

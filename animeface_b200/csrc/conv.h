@@ -67,7 +67,7 @@ long long conv_packed_bytes_halo(int co, int ci, int k);
 
 // bf16 pair-planes operands (planes.cu): TMA -> tcgen05 without a transform pass
 bool conv_halo_pl_supported(int n, int h, int w, int ci, int co, int k);
-int conv_fwd_halo_pl(const void* x_planes, const ConvParams& p, cudaStream_t st);            // p.x unused; weight packed as impl 4
+int conv_fwd_halo_pl(const void* x_planes, const ConvParams& p, int accumulate, cudaStream_t st);   // p.x unused; weight packed as impl 4
 bool wgrad_pl_supported(int n, int h, int w, int ci, int co, int k);
 long long wgrad_pl_workspace_bytes(int n, int h, int w, int ci, int co, int k);
 int conv_wgrad_pl(const void* x_planes, const void* gy_planes, float* dw, void* workspace, int n, int h, int w, int ci, int co, int k,

@@ -43,6 +43,7 @@ struct Params {
     int nkb;
     int act;
     float alpha, gain;
+    int accumulate;          // y += result (the skip branch's data gradient lands on top of the main branch's)
 };
 
 template <int BN>
@@ -193,10 +194,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_halo_pl_kernel(const __grid_
                     }
                     if (inside) {
                         const int cb = n0 + cbase;
-                        if (p.ys[1] == 1) st4(yrow + cb, make_float4(o[0], o[1], o[2], o[3]));
-                        else {
+                        if (p.ys[1] == 1) {
+                            if (p.accumulate) { const float4 t = *reinterpret_cast<const float4*>(yrow + cb); o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w; }
+                            st4(yrow + cb, make_float4(o[0], o[1], o[2], o[3]));
+                        } else {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) yrow[(long long)(cb + e) * p.ys[1]] = o[e];
+                            for (int e = 0; e < 4; ++e) {
+                                float* dst = yrow + (long long)(cb + e) * p.ys[1];
+                                *dst = p.accumulate ? *dst + o[e] : o[e];
+                            }
                         }
                     }
                 }
@@ -239,7 +245,7 @@ bool conv_halo_pl_supported(int n, int h, int w, int ci, int co, int k) {
     return conv_halo_supported(n, h, w, ci, co, k);
 }
 
-int conv_fwd_halo_pl(const void* x_planes, const ConvParams& p, cudaStream_t st) {
+int conv_fwd_halo_pl(const void* x_planes, const ConvParams& p, int accumulate, cudaStream_t st) {
     if (!conv_halo_pl_supported(p.n, p.h, p.w, p.ci, p.co, p.k)) return fail(SG2_ENOTSUP, "conv_fwd_halo_pl: unsupported shape");
     const int pad = p.k >> 1;
     CUtensorMap map;
@@ -256,7 +262,7 @@ int conv_fwd_halo_pl(const void* x_planes, const ConvParams& p, cudaStream_t st)
     const int bn = halopl::pick_bn(p.co);
     tp.n_tiles = p.co / bn;
     tp.nkb = (p.ci + 63) / 64;
-    tp.act = p.act; tp.alpha = p.alpha; tp.gain = p.gain;
+    tp.act = p.act; tp.alpha = p.alpha; tp.gain = p.gain; tp.accumulate = accumulate;
     dim3 grid((unsigned)std::min(tp.m_tiles * tp.n_tiles, num_sms()));
     if (bn == 128) return halopl::launch<128>(map, tp, grid, st);
     if (bn == 64) return halopl::launch<64>(map, tp, grid, st);

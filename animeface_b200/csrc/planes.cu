@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256) bwd_prep_planes_kernel(const float* __res
                                                               const float* __restrict__ noise, const float* __restrict__ bias,
                                                               const float* __restrict__ d, __nv_bfloat16* __restrict__ planes,
                                                               long long plane_stride, float* __restrict__ part_gb, float* __restrict__ part_gd,
-                                                              int n, int hw, int c, int slice, float alpha) {
+                                                              int n, int hw, int c, int slice, float alpha, int pool_w, float gscale) {
     __shared__ float sh[16][68];
     const int q = threadIdx.x & 15, pl = threadIdx.x >> 4;
     const int c0 = blockIdx.x * 64 + q * 4, b = blockIdx.y;
@@ -69,9 +69,15 @@ __global__ void __launch_bounds__(256) bwd_prep_planes_kernel(const float* __res
         const float4 dv = d ? ldg4(d + (long long)b * c + c0) : make_float4(1.f, 1.f, 1.f, 1.f);
         const float4 bv = bias ? ldg4(bias + c0) : f4zero();
         const float inv_alpha = 1.f / alpha;
+        // pool_w > 0: gy is the gradient of a 2x2 average pooling's OUTPUT ([n, hw/4, c], full-resolution width pool_w): the
+        // pooling adjoint (broadcast over the 2x2 window, times gscale) is applied while reading, so the full-size gradient is
+        // never written or read
+        const long long gbase = pool_w > 0 ? (long long)b * (hw >> 2) * c + c0 : base;
         for (int i = beg + pl; i < end; i += 16) {
             const long long o = base + (long long)i * c;
-            const float4 g = ldg4(gy + o);
+            long long go = o;
+            if (pool_w > 0) { const int py = i / pool_w, px = i - py * pool_w; go = gbase + ((long long)(py >> 1) * (pool_w >> 1) + (px >> 1)) * c; }
+            const float4 g = scale4(ldg4(gy + go), gscale);
             float4 gu = g, u = f4zero();
             if (y) {
                 const float4 yv = ldg4(y + o);
@@ -138,11 +144,13 @@ extern "C" int64_t sg2_bwd_prep_planes_workspace(int n, int hw, int c) {
 
 extern "C" int sg2_bwd_prep_planes(const float* gy, const float* y, const float* noise, const float* bias, const float* d,
                                    void* planes, float* gb, float* gd, void* workspace,
-                                   int n, int hw, int c, float alpha, sg2_stream_t stream) {
+                                   int n, int hw, int c, float alpha, int pool_w, float gscale, sg2_stream_t stream) {
     SG2_REQUIRE(gy && planes && gb && workspace, "bwd_prep_planes: null pointer");
     SG2_REQUIRE(n > 0 && hw > 0 && c > 0 && c % 4 == 0, "bwd_prep_planes: need n,hw > 0 and C %% 4 == 0 (C=%d)", c);
     SG2_REQUIRE(alpha != 0.f, "bwd_prep_planes: alpha must be non-zero (the activation is inverted from y)");
     SG2_REQUIRE(!gd || (d && y), "bwd_prep_planes: gd requested without d / y");
+    SG2_REQUIRE(pool_w == 0 || (pool_w > 0 && pool_w % 2 == 0 && hw % pool_w == 0 && (hw / pool_w) % 2 == 0),
+                "bwd_prep_planes: pooled gradient needs an even full-resolution width and height (w=%d, hw=%d)", pool_w, hw);
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid; int slice;
     pick_grid_pl(n, hw, c, grid, slice);
@@ -150,7 +158,7 @@ extern "C" int sg2_bwd_prep_planes(const float* gy, const float* y, const float*
     float* part_gb = (float*)workspace;
     float* part_gd = gd ? part_gb + (long long)grid.z * nc : nullptr;
     bwd_prep_planes_kernel<<<grid, 256, 0, st>>>(gy, y, noise, bias, d, (__nv_bfloat16*)planes, (long long)n * hw * c, part_gb, part_gd,
-                                                 n, hw, c, slice, alpha);
+                                                 n, hw, c, slice, alpha, pool_w, gscale);
     int rc = launched("bwd_prep_planes");
     if (rc) return rc;
     const int blocks = (int)ceil_div(nc, 256);

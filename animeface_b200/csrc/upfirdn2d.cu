@@ -296,15 +296,28 @@ __global__ void __launch_bounds__(256) upfirdn2d_ring_kernel(UpfirdnParams p) {
     }
 }
 
-template <class V, int FH, int FW, int DOWN, int COLS>
-static int launch_ring_cols(const UpfirdnParams& p, cudaStream_t st) {
-    constexpr int STRIP = 16;       // 32 halves the halo re-read but leaves the 257-row images of U4 with a nearly empty 9th strip: slower
+template <class V, int FH, int FW, int DOWN, int COLS, int STRIP>
+static int launch_ring_strip(const UpfirdnParams& p, cudaStream_t st) {
     constexpr bool NHWC = sizeof(V) == 16;
     dim3 grid;
     if (NHWC) grid = dim3((unsigned)ceil_div(ceil_div(p.out_w, COLS), 256 / (p.c / 4)), (unsigned)ceil_div(p.out_h, STRIP), (unsigned)p.n);
     else grid = dim3((unsigned)ceil_div(ceil_div(p.out_w, COLS) * ceil_div(p.out_h, STRIP), 256), 1u, (unsigned)(p.n * p.c));
     upfirdn2d_ring_kernel<V, FH, FW, DOWN, COLS, STRIP><<<grid, 256, 0, st>>>(p);
     return launched("upfirdn2d_ring");
+}
+
+template <class V, int FH, int FW, int DOWN, int COLS>
+static int launch_ring_cols(const UpfirdnParams& p, cudaStream_t st) {
+    // Rows per strip: a strip re-reads FH - DOWN halo rows, so 16 rows cost 19 % extra reads for the 4x4 blur and 32 rows 9 %;
+    // but the strip body is fully unrolled, and an image of 257 rows (U4: 256 + the blur's padding) would leave a 9th strip of 32
+    // with one row.  33 rows cut it into 8 strips.  Small images keep 16 (more blocks).  SG2_UPF_STRIP overrides (sweep).
+    static int forced = 0;
+    if (!forced) { const char* e = getenv("SG2_UPF_STRIP"); forced = e ? atoi(e) : -1; }
+    int strip = forced > 0 ? forced : (p.out_h >= 128 ? (p.out_h % 32 == 0 ? 32 : (p.out_h % 33 <= 1 || p.out_h % 32 <= 1 ? 33 : 32)) : 16);
+    if (DOWN != 1 && forced <= 0) strip = 16;
+    if (strip == 33) return launch_ring_strip<V, FH, FW, DOWN, COLS, 33>(p, st);
+    if (strip == 32) return launch_ring_strip<V, FH, FW, DOWN, COLS, 32>(p, st);
+    return launch_ring_strip<V, FH, FW, DOWN, COLS, 16>(p, st);
 }
 
 template <class V, int FH, int FW, int DOWN>

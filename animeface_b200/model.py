@@ -191,6 +191,11 @@ class DBlock(nn.Module):
         self.skip = Conv2d('elr', in_channels, out_channels, 1)
 
     def forward(self, x):
+        if len(self.block) == 4 and isinstance(self.down, Downsample2x) and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0:
+            # the standard block (two convolutions) as one autograd node: ops.conv2d.DBlockFn
+            c1, c2, sk = self.block[0], self.block[2], self.skip
+            return C.dblock(x, c1.layer.weight, c1.layer.bias, c2.layer.weight, c2.layer.bias, sk.layer.weight, sk.layer.bias,
+                            c1.coef, c2.coef, sk.coef, SLOPE, 1.0 / math.sqrt(2.0))
         t = C.conv2d_bias_act(x, self.skip.layer.weight, self.skip.layer.bias, self.skip.coef, None)
         for i in range(0, len(self.block), 2):
             conv = self.block[i]

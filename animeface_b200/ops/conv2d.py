@@ -176,11 +176,15 @@ def _split_planes(x, scale=None):
     return planes
 
 
-def _bwd_prep_planes(gy, y, slope, noise=None, bias=None, d=None):
+def _bwd_prep_planes(gy, y, slope, noise=None, bias=None, d=None, pooled=False, gscale=1.0):
     """One pass over (gy, y): gu = gy * lrelu'(y) (slope None: gu = gy, y is not read); returns (planes of gu * d, gb [co],
-    gd [n,co] or None).  The per-(sample, channel) sums are reduced in a fixed order (deterministic)."""
+    gd [n,co] or None).  The per-(sample, channel) sums are reduced in a fixed order (deterministic).
+    pooled: gy is the gradient of the 2x2 average pooling that follows the layer (half the resolution); its adjoint
+    (broadcast * gscale) is applied while reading."""
     lib = _lib.load()
     n, co, h, wd = gy.shape
+    if pooled:
+        h, wd = 2 * h, 2 * wd
     gy = _cl(gy)
     yc = None if (slope is None and d is None) else _cl(y)      # y gives the leaky-ReLU sign and, for gd, the accumulator
     planes = torch.empty((2, n, h, wd, co), dtype=torch.bfloat16, device=gy.device)
@@ -191,22 +195,29 @@ def _bwd_prep_planes(gy, y, slope, noise=None, bias=None, d=None):
     noise, bias, d = f32(noise), (None if bias is None else f32(bias).reshape(-1)), f32(d)
     _lib.check(lib.sg2_bwd_prep_planes(gy.data_ptr(), _lib.ptr(yc), _lib.ptr(noise), _lib.ptr(bias), _lib.ptr(d), planes.data_ptr(),
                                        gb.data_ptr(), _lib.ptr(gd), ws.data_ptr(), n, h * wd, co,
-                                       float(slope if slope is not None else 1.0), _lib.stream_ptr(gy)), 'sg2_bwd_prep_planes')
+                                       float(slope if slope is not None else 1.0), wd if pooled else 0, float(gscale),
+                                       _lib.stream_ptr(gy)), 'sg2_bwd_prep_planes')
     return planes, gb.sum(0), gd
 
 
-def _conv_planes(xp, w, coef, transpose):
-    """y = conv(x, w*coef) (transpose: the data gradient) with x given as pair planes [2][n,h,w,cin]; bf16x3 halo kernel."""
+def _conv_planes(xp, w, coef, transpose, accumulate_into=None):
+    """y = conv(x, w*coef) (transpose: the data gradient) with x given as pair planes [2][n,h,w,cin]; bf16x3 halo kernel.
+    accumulate_into: an existing channels_last result tensor the convolution is ADDED to (returned)."""
     lib = _lib.load()
     co, ci, k, _ = w.shape
     cin, cout = (co, ci) if transpose else (ci, co)
     _, n, h, wd, cx = xp.shape
     assert cx == cin
     packed = _pack(w, coef, transpose, IMPL_HALO)
-    y = torch.empty_strided((n, cout, h, wd), (h * wd * cout, 1, wd * cout, cout), dtype=torch.float32, device=xp.device)
+    if accumulate_into is not None:
+        y = accumulate_into
+        assert tuple(y.shape) == (n, cout, h, wd) and y.stride() == (h * wd * cout, 1, wd * cout, cout)
+    else:
+        y = torch.empty_strided((n, cout, h, wd), (h * wd * cout, 1, wd * cout, cout), dtype=torch.float32, device=xp.device)
     with _timed('dgrad' if transpose else 'fwd', 2.0 * n * h * wd * cin * cout * k * k):
         _lib.check(lib.sg2_conv2d_fwd_planes(xp.data_ptr(), packed.data_ptr(), y.data_ptr(), _lib.strides4(y), n, h, wd, cin, cout, k,
-                                             None, None, 1, 0.0, 1.0, _lib.stream_ptr(xp)), 'sg2_conv2d_fwd_planes')
+                                             None, None, 1, 0.0, 1.0, 1 if accumulate_into is not None else 0, _lib.stream_ptr(xp)),
+                   'sg2_conv2d_fwd_planes')
     return y
 
 
@@ -366,6 +377,81 @@ def conv2d_bias_act(x, w, b, coef: float = 1.0, slope: float | None = 0.2, gain:
     slope=None -> no activation (the DBlock skip conv, model.py:201)."""
     assert gain > 0
     return ConvBiasActFn.apply(x, w, b, float(coef), slope, float(gain))
+
+
+# ----------------------------------------------------------------------------------------------
+# The whole residual discriminator block (DBlock.forward, implementations/StyleGAN2/model.py:204-212) as ONE autograd node:
+#   h1 = lrelu(conv3x3(x) + b1);  h2 = lrelu(conv3x3(h1) + b2);  t = conv1x1(x) + bs;  out = alpha * (avgpool2(h2) + avgpool2(t))
+# The forward is the same four launches as the separate ops.  What the single node buys is the first-order backward: the
+# pooling adjoint is folded into the two leaky-ReLU-gradient passes that follow it (the full-resolution gradient of the
+# pooling input is never written or read), x is split into planes once for the two weight gradients that consume it, and the
+# skip branch's data gradient accumulates in the epilogue of its kernel instead of a separate add.  Under create_graph (R1)
+# the backward is composed from the differentiable families, exactly like ConvBiasActFn.
+
+def _composed_conv_backward(x, w, y, gy, coef, slope, need_gx, need_gw, need_gb):
+    from .bias_act import act_grad
+    gu = act_grad(gy, y, slope) if slope is not None else gy
+    gx = Conv2dTransposeFn.apply(gu, w, coef) if need_gx else None
+    gw = Conv2dWgradFn.apply(x, gu, w.shape[2], coef) if need_gw else None
+    gb = gu.sum((0, 2, 3)) if need_gb else None
+    return gx, gw, gb
+
+
+class DBlockFn(torch.autograd.Function):
+    @staticmethod
+    @amp_fwd
+    def forward(ctx, x, w1, b1, w2, b2, ws, bs, coef1, coef2, coefs, slope, alpha):
+        from .resample import _avgpool
+        h1 = _conv_raw(x, w1, coef1, False, bias=b1, slope=slope)
+        h2 = _conv_raw(h1, w2, coef2, False, bias=b2, slope=slope)
+        t = _conv_raw(x, ws, coefs, False, bias=bs)
+        out = _avgpool(h2, t, alpha, False)
+        ctx.cfg = (coef1, coef2, coefs, slope, alpha)
+        ctx.save_for_backward(x, w1, w2, ws, h1, h2)
+        return out
+
+    @staticmethod
+    @amp_bwd
+    def backward(ctx, g):
+        from .resample import AvgPool2AdjFn
+        x, w1, w2, ws, h1, h2 = ctx.saved_tensors
+        coef1, coef2, coefs, slope, alpha = ctx.cfg
+        need = ctx.needs_input_grad
+        n, ci, h, wd = x.shape
+        co = w1.shape[0]
+        fast = (not torch.is_grad_enabled() and co % 4 == 0 and h % 2 == 0 and wd % 2 == 0
+                and _planes_ok(n, h, wd, co, ci, 3, False) and _planes_ok(n, h, wd, co, co, 3, False) and _planes_ok(n, h, wd, co, ci, 1, False)
+                and _planes_ok(n, h, wd, ci, co, 3, True) and _planes_ok(n, h, wd, co, co, 3, True) and _planes_ok(n, h, wd, ci, co, 1, True))
+        if not fast:
+            gf = AvgPool2AdjFn.apply(g, alpha)
+            gh1, gw2, gb2 = _composed_conv_backward(h1, w2, h2, gf, coef2, slope, True, need[3], need[4])
+            gx1, gw1, gb1 = _composed_conv_backward(x, w1, h1, gh1, coef1, slope, need[0], need[1], need[2])
+            gx2, gws, gbs = _composed_conv_backward(x, ws, None, gf, coefs, None, need[0], need[5], need[6])
+            gx = gx1 + gx2 if need[0] else None
+            return gx, gw1, gb1, gw2, gb2, gws, gbs, None, None, None, None, None
+        gscale = 0.25 * alpha
+        gu2p, gb2, _ = _bwd_prep_planes(g, h2, slope, pooled=True, gscale=gscale)          # d out / d h2, masked by lrelu'(h2)
+        gtp, gbs, _ = _bwd_prep_planes(g, None, None, pooled=True, gscale=gscale)           # d out / d t (no activation)
+        gh1 = _conv_planes(gu2p, w2, coef2, True)
+        gu1p, gb1, _ = _bwd_prep_planes(gh1, h1, slope)
+        gx = None
+        if need[0]:
+            gx = _conv_planes(gu1p, w1, coef1, True)
+            gx = _conv_planes(gtp, ws, coefs, True, accumulate_into=gx)
+        gw1 = gw2 = gws = None
+        if need[1] or need[5]:
+            xp = _split_planes(x)
+            gw1 = _wgrad_planes(xp, gu1p, 3, coef1) if need[1] else None
+            gws = _wgrad_planes(xp, gtp, 1, coefs) if need[5] else None
+        if need[3]:
+            gw2 = _wgrad_planes(_split_planes(h1), gu2p, 3, coef2)
+        return (gx, gw1, gb1 if need[2] else None, gw2, gb2 if need[4] else None, gws, gbs if need[6] else None,
+                None, None, None, None, None)
+
+
+def dblock(x, w1, b1, w2, b2, ws, bs, coef1, coef2, coefs, slope=0.2, alpha=0.7071067811865476):
+    """DBlock.forward (model.py:204-212) for the standard block (two 3x3 convolutions, 1x1 skip, average pooling)."""
+    return DBlockFn.apply(x, w1, b1, w2, b2, ws, bs, float(coef1), float(coef2), float(coefs), float(slope), float(alpha))
 
 
 # ----------------------------------------------------------------------------------------------

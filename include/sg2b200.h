@@ -207,7 +207,10 @@ int sg2_modconv_bwd_prep(const float* gy, const float* y, const float* noise, co
  * sg2_split_planes:    planes = split(x * scale[b,c])   (scale may be NULL)                        c % 4 == 0
  * sg2_bwd_prep_planes: sg2_modconv_bwd_prep with g_acc written as planes and DETERMINISTIC per-(sample, channel) sums:
  *                      gb[n,c] = sum_hw gu, gd[n,c] = sum_hw gu * acc (NULL = skip); y NULL = no activation (gu = gy);
- *                      workspace: sg2_bwd_prep_planes_workspace(n, hw, c) bytes.
+ *                      workspace: sg2_bwd_prep_planes_workspace(n, hw, c) bytes.  pool_w > 0: gy is the gradient of the 2x2
+ *                      average pooling that follows the layer (implementations/StyleGAN2/model.py:209-212), [n, hw/4, c] with
+ *                      full-resolution width pool_w; its adjoint (broadcast * gscale) is applied on the fly.  gscale also
+ *                      scales an ordinary gy.  sg2_conv2d_fwd_planes(accumulate = 1) adds into y instead of overwriting it.
  * sg2_conv2d_fwd_planes: y = gain * act(out_scale * conv(x, w) + bias) with x given as planes [2][n,h,w,ci]
  *                      (ci % 64 == 0); packed_w from sg2_conv2d_pack_weight(impl = 4) -- with transpose = 1 this is the
  *                      data gradient.  sg2_conv2d_planes_supported(.., wgrad = 0) tells whether the shape is taken.
@@ -218,12 +221,12 @@ int sg2_split_planes(const float* x, const float* scale, void* planes, int n, in
 int64_t sg2_bwd_prep_planes_workspace(int n, int hw, int c);
 int sg2_bwd_prep_planes(const float* gy, const float* y, const float* noise, const float* bias, const float* d,
                         void* planes, float* gb, float* gd, void* workspace,
-                        int n, int hw, int c, float alpha, sg2_stream_t stream);
+                        int n, int hw, int c, float alpha, int pool_w, float gscale, sg2_stream_t stream);
 int sg2_conv2d_planes_supported(int n, int h, int w, int ci, int co, int k, int wgrad);
 int sg2_conv2d_fwd_planes(const void* x_planes, const void* packed_w, float* y, const int64_t y_strides[4],
                           int n, int h, int w, int ci, int co, int k,
                           const float* out_scale, const float* bias, int act, float alpha, float gain,
-                          sg2_stream_t stream);
+                          int accumulate, sg2_stream_t stream);
 int64_t sg2_conv2d_wgrad_planes_workspace(int n, int h, int w, int ci, int co, int k);
 int sg2_conv2d_wgrad_planes(const void* x_planes, const void* gy_planes, float* dw, void* workspace,
                             int n, int h, int w, int ci, int co, int k, float coef, int accumulate,

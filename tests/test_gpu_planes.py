@@ -168,3 +168,34 @@ def test_modulated_conv_backward_planes_vs_fp32_operands():
             C.planes_enabled = True
     for a, o in zip(*outs):
         assert _rel(a, o) < 2e-5, _rel(a, o)
+
+
+@pytest.mark.parametrize('ci,co,hw', [(64, 128, 32), (32, 64, 64), (128, 128, 16)])
+def test_dblock_single_node_fast_backward_vs_composed(ci, co, hw):
+    """DBlockFn: pooled leaky-ReLU-gradient passes + shared x planes + accumulating skip data gradient (first-order fast path)
+    against the composition of the differentiable families (planes off), and against plain torch."""
+    import math
+    from animeface_b200.ops import conv2d as C
+    _setup()
+    g = torch.Generator(device=DEV).manual_seed(ci + co)
+    x = _cl(4, ci, hw, hw, seed=21).requires_grad_(True)
+    mk = lambda *s: torch.randn(*s, device=DEV, generator=g).requires_grad_(True)
+    w1, w2, ws = mk(co, ci, 3, 3), mk(co, co, 3, 3), mk(co, ci, 1, 1)
+    b1, b2, bs = mk(co), mk(co), mk(co)
+    c1, c2, cs = 1 / math.sqrt(ci * 9), 1 / math.sqrt(co * 9), 1 / math.sqrt(ci)
+    gy = _cl(4, co, hw // 2, hw // 2, seed=22)
+    params = (x, w1, b1, w2, b2, ws, bs)
+    outs = []
+    for enabled in (True, False):
+        C.planes_enabled = enabled
+        try:
+            y = C.dblock(x, w1, b1, w2, b2, ws, bs, c1, c2, cs)
+            outs.append((y.detach(),) + torch.autograd.grad(y, params, gy))
+        finally:
+            C.planes_enabled = True
+    h = F.leaky_relu(F.conv2d(x, w1 * c1, b1, padding=1), 0.2)
+    h = F.leaky_relu(F.conv2d(h, w2 * c2, b2, padding=1), 0.2)
+    ref_y = (F.avg_pool2d(h, 2) + F.avg_pool2d(F.conv2d(x, ws * cs, bs), 2)) / math.sqrt(2.0)
+    ref = (ref_y.detach(),) + torch.autograd.grad(ref_y, params, gy)
+    for name, a, o, r in zip(('y', 'gx', 'gw1', 'gb1', 'gw2', 'gb2', 'gws', 'gbs'), outs[0], outs[1], ref):
+        assert _rel(a, o) < 2e-5 and _rel(a, r) < 5e-5, (name, _rel(a, o), _rel(a, r))
