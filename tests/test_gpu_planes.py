@@ -197,5 +197,10 @@ def test_dblock_single_node_fast_backward_vs_composed(ci, co, hw):
     h = F.leaky_relu(F.conv2d(h, w2 * c2, b2, padding=1), 0.2)
     ref_y = (F.avg_pool2d(h, 2) + F.avg_pool2d(F.conv2d(x, ws * cs, bs), 2)) / math.sqrt(2.0)
     ref = (ref_y.detach(),) + torch.autograd.grad(ref_y, params, gy)
+    # fast vs composed share the forward (same leaky-ReLU masks): they must agree to kernel round-off.  Against torch the masks
+    # can differ in the sign of a handful of near-zero pre-activations (each flip moves ~600 gradient elements by a few
+    # percent of their scale), so that comparison is in the L2 norm: a wrong tap / layout / scale would be O(1) there.
+    l2 = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
     for name, a, o, r in zip(('y', 'gx', 'gw1', 'gb1', 'gw2', 'gb2', 'gws', 'gbs'), outs[0], outs[1], ref):
-        assert _rel(a, o) < 2e-5 and _rel(a, r) < 5e-5, (name, _rel(a, o), _rel(a, r))
+        assert _rel(a, o) < 2e-5 and l2(a, r) < 5e-3, (name, _rel(a, o), l2(a, r))
+    assert _rel(outs[0][0], ref[0]) < 5e-5
