@@ -7,17 +7,16 @@ thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 long long* g_trace = nullptr;
 
-// impl codes: 0 auto, 1 fp32 SIMT, 2 tcgen05 bf16x3 (per-tap loads), 3 tcgen05 tf32x3+promotion (per-tap loads),
-// 4 tcgen05 bf16x3 halo kernel, 5 tcgen05 tf32x3+promotion halo kernel.  `precise` steers auto towards 3/5.
+// impl codes: 0 auto, 1 fp32 kernels (SIMT implicit GEMM / thin one-pass kernels), 4 tcgen05 bf16x3 halo kernel, 5 tcgen05
+// fp32-class (fp16 big/small + promotion) halo kernel.  `precise` steers auto towards 5.  (Codes 2 and 3 were round 1's first
+// generation, one TMA box per tap; the halo kernels now take every output width that is a multiple of 32, so they are gone.)
 // Returns the implementation that will run, or -1 when an explicitly requested one does not take the shape.
 static int resolve_impl(int impl, int precise, int n, int h, int w, int ci, int co, int k) {
-    const bool tc_ok = conv_tc_supported(n, h, w, ci, co, k);
     const bool halo_ok = conv_halo_supported(n, h, w, ci, co, k);
     if (impl == 1) return 1;
-    if (impl == 2 || impl == 3) return tc_ok ? impl : -1;
+    if (impl == 2 || impl == 3) return -1;
     if (impl == 4 || impl == 5) return halo_ok ? impl : -1;
-    if (halo_ok) return precise ? 5 : 4;
-    return tc_ok ? (precise ? 3 : 2) : 1;
+    return halo_ok ? (precise ? 5 : 4) : 1;
 }
 }  // namespace sg2
 
@@ -42,13 +41,9 @@ extern "C" int sg2_conv2d_select_impl(int n, int h, int w, int ci, int co, int k
 extern "C" int64_t sg2_conv2d_packed_size(int co, int ci, int k, int impl) {
     if (co <= 0 || ci <= 0 || (k != 1 && k != 3)) return -1;
     long long simt = (long long)co * ci * k * k * 4;
-    long long tcb = conv_packed_bytes_tc(co, ci, k);
-    long long tc32 = conv_packed_bytes_tc32(co, ci, k);
     long long hl = conv_packed_bytes_halo(co, ci, k);
     (void)impl;
-    long long m = simt > tcb ? simt : tcb;
-    m = m > tc32 ? m : tc32;
-    return 256 + (m > hl ? m : hl);
+    return 256 + (simt > hl ? simt : hl);
 }
 
 static int pick_impl_for_pack(int co, int ci, int k, int transpose, int impl) {
@@ -66,9 +61,8 @@ extern "C" int sg2_conv2d_pack_weight(const float* w, void* packed, int co, int 
     cudaStream_t st = (cudaStream_t)stream;
     void* body = (char*)packed + 256;
     if (use == 1) return conv_pack_simt(w, (float*)body, co, ci, k, coef, transpose, st);
-    if (use == 3) return conv_pack_tc32(w, body, co, ci, k, coef, transpose, st);
     if (use == 4 || use == 5) return conv_pack_halo(w, body, co, ci, k, coef, transpose, use == 5, st);
-    return conv_pack_tc(w, body, co, ci, k, coef, transpose, st);
+    return fail(SG2_ENOTSUP, "conv2d_pack_weight: implementation %d does not exist", use);
 }
 
 extern "C" int sg2_conv2d_fwd(const float* x, const void* packed_w, float* y, const int64_t y_strides[4],
@@ -85,8 +79,8 @@ extern "C" int sg2_conv2d_fwd(const float* x, const void* packed_w, float* y, co
     // sg2_conv2d_select_impl and pass the same explicit code to both.  impl = 0 resolves as "precise forward".
     const int packed_for = resolve_impl(impl, 1, n, h, w, ci, co, k);
     if (packed_for < 0) return fail(SG2_ENOTSUP, "conv2d_fwd: tcgen05 path does not take n=%d h=%d w=%d ci=%d co=%d k=%d", n, h, w, ci, co, k);
-    if (impl == 0 && packed_for == 1 && conv_tc_supported(1, 16, 16, ci, co, k))
-        return fail(SG2_ENOTSUP, "conv2d_fwd: image size %dx%d needs the SIMT kernel; pack and call with impl=1", h, w);
+    if (impl == 0 && packed_for == 1 && conv_halo_supported(1, 16, 16, ci, co, k))
+        return fail(SG2_ENOTSUP, "conv2d_fwd: image size %dx%d needs the fp32 kernel; pack and call with impl=1", h, w);
     ConvParams p;
     p.x = x; p.wp = (const char*)packed_w + 256; p.y = y;
     for (int i = 0; i < 4; ++i) p.ys[i] = y_strides[i];
@@ -94,8 +88,6 @@ extern "C" int sg2_conv2d_fwd(const float* x, const void* packed_w, float* y, co
     p.in_scale = in_scale; p.out_scale = out_scale; p.bias = bias; p.noise = noise;
     p.act = act; p.alpha = alpha; p.gain = gain;
     cudaStream_t st = (cudaStream_t)stream;
-    if (packed_for == 2) return conv_fwd_tc(p, st);
-    if (packed_for == 3) return conv_fwd_tc32(p, st);
     if (packed_for == 4 || packed_for == 5) return conv_fwd_halo(p, packed_for == 5, st);
     return conv_fwd_simt(p, st);
 }

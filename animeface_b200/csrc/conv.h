@@ -46,18 +46,9 @@ int conv_fwd_thin(const ConvParams& p, cudaStream_t st);
 int conv_wgrad_thin(const WgradParams& p, cudaStream_t st);
 int wgrad_parts_thin(const WgradParams& p);     // 0 when the thin kernel does not take the shape
 
-// tcgen05 path (conv_tc.cu)
-bool conv_tc_supported(int n, int h, int w, int ci, int co, int k);
+// tcgen05 weight gradient on fp32 operands (wgrad_tc.cu)
 bool wgrad_tc_supported(int n, int h, int w, int ci, int co, int k);
-int conv_fwd_tc(const ConvParams& p, cudaStream_t st);
 int conv_wgrad_tc(WgradParams p, int accumulate, cudaStream_t st);
-int conv_pack_tc(const float* w, void* wp, int co, int ci, int k, float coef, int transpose, cudaStream_t st);
-long long conv_packed_bytes_tc(int co, int ci, int k);
-
-// tcgen05 path, fp32-class precision (conv_tc32.cu): forward convolutions
-int conv_fwd_tc32(const ConvParams& p, cudaStream_t st);
-int conv_pack_tc32(const float* w, void* wp, int co, int ci, int k, float coef, int transpose, cudaStream_t st);
-long long conv_packed_bytes_tc32(int co, int ci, int k);
 
 // tcgen05 path, halo variant (conv_halo.cu): patch loaded/converted once per tile, taps = shifted descriptor windows
 bool conv_halo_supported(int n, int h, int w, int ci, int co, int k);

@@ -1,8 +1,8 @@
 // tcgen05 implicit-GEMM convolution, "halo" variant: the activation patch of a tile is loaded and converted ONCE and
 // the k*k taps are shifted windows of it, addressed through the UMMA shared-memory descriptors.
 //
-// conv_tc.cu / conv_tc32.cu load one TMA box per (tap, channel block): every input element crosses L2->SMEM and the
-// fp32->split conversion 9 times for a 3x3 kernel, which makes the low-channel, high-resolution layers of the path
+// Round 1's first kernels loaded one TMA box per (tap, channel block): every input element crossed L2->SMEM and the
+// fp32->split conversion 9 times for a 3x3 kernel, which made the low-channel, high-resolution layers of the path
 // (64->64 @256^2 etc.) L2- and conversion-bound.  Here, per CTA tile of 8 x 16 pixels and per block of input channels:
 //   TMA      one box [32 ch, 8+2p, 16+2p, 1] (p = k/2; out-of-bounds -> 0 = zero padding) into a SWIZZLE_128B fp32 slot
 //   xform    8 warps: (style scale) -> split planes, written as a NON-swizzled K-major operand image
@@ -15,7 +15,7 @@
 //            A fetched from shared memory twice instead of three times (the operand fetch paces the MMAs of this kernel)
 // PRECISE = false: bf16x3 (hi/lo planes, kind::f16, 64 channels per block); result = lower + upper half -> data gradients
 // PRECISE = true : fp16x3 + promotion: big = rn_f16(v), small = rn_f16((v - big) * 2^11) (22 mantissa bits together, like
-//                  the tf32 pair of conv_tc32.cu but at the fp16 MMA rate); lower half D1 = big*big, upper half D2 =
+//                  a tf32 pair but at the fp16 MMA rate); lower half D1 = big*big, upper half D2 =
 //                  big*small + small*big; every `promo_taps` taps (default 2 = 8 chained big*big MMAs -- the tensor core
 //                  truncates its accumulator per MMA) the segment is promoted into fp32 registers (acc += D1 + 2^-11 D2)
 //                  and its TMEM buffer handed back at once                              -> forward convs, fp32-class
@@ -488,7 +488,8 @@ __global__ void conv_pack_halo_kernel(const float* __restrict__ w, unsigned char
     }
 }
 
-static int pick_bn(int co) { return co % 128 == 0 ? 128 : (co == 64 ? 64 : (co == 32 ? 32 : 0)); }
+// output-channel tile: every multiple of 32 has one (n_tiles = co / BN)
+static int pick_bn(int co) { return co % 128 == 0 ? 128 : (co % 64 == 0 ? 64 : (co % 32 == 0 ? 32 : 0)); }
 
 template <int BN, bool PRECISE>
 static int launch(const CUtensorMap& map, const Params& tp, dim3 grid, cudaStream_t st) {
@@ -515,7 +516,7 @@ bool conv_halo_supported(int n, int h, int w, int ci, int co, int k) {
     // the StyleGAN3-style discriminator) ...
     if (((w % halo::TW) == 0 && (h % halo::TH) == 0) || (w >= 32 && h >= 32)) return true;
     // ... or small images (4^2, 8^2) whose tiles, however empty, all fit the machine at once: one 8 x 16 tile per image
-    // wastes most of its rows, but every CTA runs the full-rate pipeline in a single wave, which beats the per-tap kernels
+    // wastes most of its rows, but every CTA runs the full-rate pipeline in a single wave, which beat round 1's per-tap kernels
     const long long tiles = (long long)((w + halo::TW - 1) / halo::TW) * ((h + halo::TH - 1) / halo::TH) * n * (co / bn);
     return w >= 4 && h >= 4 && tiles <= 2LL * num_sms();
 }

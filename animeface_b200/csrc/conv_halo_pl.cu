@@ -220,7 +220,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_halo_pl_kernel(const __grid_
     }
 }
 
-static int pick_bn(int co) { return co % 128 == 0 ? 128 : (co == 64 ? 64 : (co == 32 ? 32 : 0)); }
+// output-channel tile: every multiple of 32 has one (n_tiles = co / BN)
+static int pick_bn(int co) { return co % 128 == 0 ? 128 : (co % 64 == 0 ? 64 : (co % 32 == 0 ? 32 : 0)); }
 
 template <int BN>
 static int launch(const CUtensorMap& map, const Params& tp, dim3 grid, cudaStream_t st) {

@@ -20,7 +20,7 @@ from .._lib import amp_bwd, amp_fwd
 
 import os
 
-IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC32, IMPL_HALO, IMPL_HALO32 = 0, 1, 2, 3, 4, 5
+IMPL_AUTO, IMPL_SIMT, IMPL_HALO, IMPL_HALO32 = 0, 1, 4, 5
 _default_impl = int(os.environ.get('SG2_CONV_IMPL', '0'))     # 0 = auto; see set_default_impl
 # experiment switch (profiles/r2_*): data-gradient / second-order convolutions on the fp32-class kernel instead of bf16x3
 _grad_precise = os.environ.get('SG2_GRAD_PRECISE', '0') == '1'
@@ -31,8 +31,8 @@ launch_log = None
 
 
 class _timed:
-    def __init__(self, kind, flops):
-        self.kind, self.flops = kind, flops
+    def __init__(self, kind, flops, label=''):
+        self.kind, self.flops, self.label = kind, flops, label
 
     def __enter__(self):
         if launch_log is not None:
@@ -43,15 +43,15 @@ class _timed:
     def __exit__(self, *exc):
         if launch_log is not None:
             self.e1.record()
-            launch_log.append((self.kind, self.flops, self.e0, self.e1))
+            launch_log.append((self.kind, self.flops, self.e0, self.e1, self.label))
 
 
 def set_default_impl(impl: int) -> None:
     """0 = auto (tcgen05 where the shape allows -- fp32-class split operands for forward convs, bf16x3 for gradients; halo
-    kernels where the image tiles by 8x16 -- else fp32 SIMT), 1 = SIMT everywhere, 2..5 = prefer that tcgen05 kernel
-    (per-tap bf16x3 / per-tap tf32x3 + promotion / halo bf16x3 / halo fp16x3 + promotion) wherever it applies."""
+    kernels where the image tiles by 8x16 -- else fp32 SIMT), 1 = fp32 kernels everywhere, 4 / 5 = prefer the bf16x3 /
+    fp16x3 + promotion halo kernel wherever it applies."""
     global _default_impl
-    assert impl in (0, 1, 2, 3, 4, 5)
+    assert impl in (0, 1, 4, 5)
     _default_impl = impl
 
 
@@ -117,7 +117,7 @@ def _conv_raw(x, w, coef, transpose, in_scale=None, out_scale=None, bias=None, n
         y = _empty_cl(n, cout, h, wd, x)
     f32 = lambda t: None if t is None else t.detach().to(torch.float32).contiguous()
     in_scale, out_scale, bias, noise = f32(in_scale), f32(out_scale), f32(bias), f32(noise)
-    with _timed('dgrad' if transpose else 'fwd', 2.0 * n * h * wd * cin * cout * k * k):
+    with _timed('dgrad' if transpose else 'fwd', 2.0 * n * h * wd * cin * cout * k * k, f'{cin}->{cout} k{k} @{h}x{wd} n{n} impl{impl}'):
         _lib.check(lib.sg2_conv2d_fwd(
             x.data_ptr(), packed.data_ptr(), y.data_ptr(), _lib.strides4(y), n, h, wd, cin, cout, k,
             _lib.ptr(in_scale), _lib.ptr(out_scale), _lib.ptr(bias), _lib.ptr(noise),
@@ -138,7 +138,7 @@ def _wgrad_raw(x, gy, k, coef, in_scale=None, out_scale=None, impl=None):
     f32 = lambda t: None if t is None else t.detach().to(torch.float32).contiguous()
     in_scale, out_scale = f32(in_scale), f32(out_scale)
     ws = _workspace(lib.sg2_conv2d_wgrad_workspace(n, h, wd, ci, co, k, impl), x.device, 'sg2_conv2d_wgrad_workspace')
-    with _timed('wgrad', 2.0 * n * h * wd * ci * co * k * k):
+    with _timed('wgrad', 2.0 * n * h * wd * ci * co * k * k, f'{ci}->{co} k{k} @{h}x{wd} n{n} fp32-operands'):
         _lib.check(lib.sg2_conv2d_wgrad(x.data_ptr(), gy.data_ptr(), dw.data_ptr(), n, h, wd, ci, co, k, float(coef),
                                         _lib.ptr(in_scale), _lib.ptr(out_scale), 0, impl, ws.data_ptr(), _lib.stream_ptr(x)),
                    'sg2_conv2d_wgrad')
@@ -214,7 +214,7 @@ def _conv_planes(xp, w, coef, transpose, accumulate_into=None):
         assert tuple(y.shape) == (n, cout, h, wd) and y.stride() == (h * wd * cout, 1, wd * cout, cout)
     else:
         y = torch.empty_strided((n, cout, h, wd), (h * wd * cout, 1, wd * cout, cout), dtype=torch.float32, device=xp.device)
-    with _timed('dgrad' if transpose else 'fwd', 2.0 * n * h * wd * cin * cout * k * k):
+    with _timed('dgrad' if transpose else 'fwd', 2.0 * n * h * wd * cin * cout * k * k, f'{cin}->{cout} k{k} @{h}x{wd} n{n} planes'):
         _lib.check(lib.sg2_conv2d_fwd_planes(xp.data_ptr(), packed.data_ptr(), y.data_ptr(), _lib.strides4(y), n, h, wd, cin, cout, k,
                                              None, None, 1, 0.0, 1.0, 1 if accumulate_into is not None else 0, _lib.stream_ptr(xp)),
                    'sg2_conv2d_fwd_planes')
@@ -228,7 +228,7 @@ def _wgrad_planes(xp, gyp, k, coef):
     co = gyp.shape[4]
     dw = torch.empty((co, ci, k, k), dtype=torch.float32, device=xp.device)
     ws = _workspace(lib.sg2_conv2d_wgrad_planes_workspace(n, h, wd, ci, co, k), xp.device, 'sg2_conv2d_wgrad_planes_workspace')
-    with _timed('wgrad', 2.0 * n * h * wd * ci * co * k * k):
+    with _timed('wgrad', 2.0 * n * h * wd * ci * co * k * k, f'{ci}->{co} k{k} @{h}x{wd} n{n} planes'):
         _lib.check(lib.sg2_conv2d_wgrad_planes(xp.data_ptr(), gyp.data_ptr(), dw.data_ptr(), ws.data_ptr(), n, h, wd, ci, co, k,
                                                float(coef), 0, _lib.stream_ptr(xp)), 'sg2_conv2d_wgrad_planes')
     return dw

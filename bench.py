@@ -25,13 +25,18 @@ sys.path.insert(0, ROOT)
 
 
 
+TOP_KERNEL = 'halo::conv_halo_kernel<128, 1> grid 148'      # largest single kernel of the step (profiles/r2e_launches.txt)
+
+
 def load_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/r2_ncu_traffic.json,
-    written by scripts/ncu_summary.py from the .ncu-rep of the same shapes); None when the file is absent."""
+    """(DRAM bytes per launch of the step's largest kernel, the per-kernel table) from the committed `ncu --set full` capture
+    (profiles/r2_ncu_traffic.json, written by scripts/ncu_summary.py from the .ncu-rep of scripts/ncu_targets.py: full layer
+    shapes, B = 32, dram__bytes_read.sum + dram__bytes_write.sum); (None, None) when the file is absent."""
     try:
-        return json.load(open(os.path.join(ROOT, 'profiles', 'r2_ncu_traffic.json')))
+        t = json.load(open(os.path.join(ROOT, 'profiles', 'r2_ncu_traffic.json')))['kernels']
+        return t.get(TOP_KERNEL, {}).get('dram_bytes'), {k: v['dram_bytes'] for k, v in t.items()}
     except Exception:
-        return None
+        return None, None
 
 
 def load_peaks():
@@ -284,15 +289,23 @@ def run_b200(args):
     value = world * B * args.steps / (ms / 1e3)
 
     # roofline of the dominant kernel family: the convolution launches (fwd/dgrad/wgrad implicit GEMMs)
-    conv_ms = sum(a.elapsed_time(b) for _, _, a, b in conv_log)
-    conv_flops = sum(f for _, f, _, _ in conv_log)
+    conv_ms = sum(a.elapsed_time(b) for _, _, a, b, _ in conv_log)
+    conv_flops = sum(f for _, f, _, _, _ in conv_log)
     achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
     by_kind = {}
-    for kind, f, a, b in conv_log:
+    by_layer = {}
+    for kind, f, a, b, label in conv_log:
         d = by_kind.setdefault(kind, [0.0, 0.0, 0])
         d[0] += f; d[1] += a.elapsed_time(b); d[2] += 1
+        d = by_layer.setdefault(f'{kind} {label}', [0.0, 0.0, 0])
+        d[0] += f; d[1] += a.elapsed_time(b); d[2] += 1
+    if args.layers and rank == 0:
+        with open(args.layers, 'w') as fh:
+            for k, v in sorted(by_layer.items(), key=lambda kv: -kv[1][1]):
+                fh.write(f'{v[1] / args.steps:8.3f} ms/step {100 * v[1] / max(conv_ms, 1e-9):5.1f}% {v[0] / max(v[1], 1e-9) / 1e9:7.1f} TF/s {v[2] / args.steps:5.1f} launches/step  {k}\n')
     roofline = dict(bound='tensor', achieved=round(achieved, 2), peak=peaks['tf'], unit='TFLOP/s',
-                    frac=round(achieved / peaks['tf'], 4), traffic=load_traffic(),
+                    frac=round(achieved / peaks['tf'], 4), traffic=load_traffic()[0], traffic_kernel=TOP_KERNEL + ' (128->128 @128^2, B=32: algorithmic 537 MB)',
+                    traffic_by_kernel=load_traffic()[1],
                     kernel='conv2d fwd/dgrad/wgrad (all launches of K steps)', measured_in=roofline_note,
                     peak_source=f"bf16_tflops_sustained of MEASURED_PEAKS.json ({peaks['src']})",
                     share_of_step=round(conv_ms / max(ms, 1e-9), 3),
@@ -369,8 +382,9 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--config', type=int, default=2, choices=[2, 4], help='BASELINE config: 2 (256 px, the metric) or 4 (512 px + ADA)')
     ap.add_argument('--batch', type=int, default=None, help='per-GPU batch (BASELINE config 2/3: 32, config 4: 16)')
-    ap.add_argument('--conv-impl', default='auto', choices=['auto', 'simt', 'tc'])
+    ap.add_argument('--conv-impl', default='auto', choices=['auto', 'simt'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--layers', default='', help='write the per-layer convolution time table of the roofline pass to this file')
     ap.add_argument('--no-graphs', dest='graphs', action='store_false', help='run the step eagerly instead of replaying CUDA graphs')
     args = ap.parse_args()
     if args.batch is None:
@@ -379,7 +393,7 @@ def main():
         run_reference(args)
         return
     from animeface_b200.ops import conv2d as C
-    C.set_default_impl(dict(auto=0, simt=1, tc=2)[args.conv_impl])
+    C.set_default_impl(dict(auto=0, simt=1)[args.conv_impl])
     run_b200(args)
 
 

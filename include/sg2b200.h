@@ -140,20 +140,18 @@ int sg2_mbstd_bwd(const float* x, const int64_t x_strides[4], const float* gy,
  *   act: 1 linear, 3 lrelu(alpha); then * gain                      (model.py:164)
  *   y = gain * act( out_scale * conv(x * in_scale, w) + bias + noise )
  * impl: 0 = auto, 1 = fp32 kernels (SIMT implicit GEMM; one-pass "thin" kernels when one side has <= 4 channels),
- *       2..5 = tcgen05 kernels:
- *   precision "bf16x3" (2, 4): fp32 operands split into bf16 hi/lo pairs, the three products hi*hi + lo*hi + hi*lo
- *       accumulated in fp32 in TMEM (~5e-6 relative) -- data and weight gradients, which are linear in their operands;
- *   precision "fp32-class" (3, 5): operands split into big/small pairs carrying 22 mantissa bits (3: tf32 pairs,
- *       5: fp16 pairs with the residual scaled by 2^11, at the full 16-bit MMA rate) and the big*big accumulator is
- *       promoted into fp32 registers every few MMAs (the tensor core truncates its accumulator per MMA):
- *       fp32-class results (~4e-7).  FORWARD convs use it: a relative input error eps flips ~0.8*eps of the
- *       leaky-ReLU signs against the fp32 reference and gradient parity degrades like sqrt(eps);
- *   data movement: 2, 3 = one TMA box per (tap, channel block) (any power-of-two image >= 4x4);
- *       4, 5 = "halo" kernels: the (8+2)x(16+2) patch of a tile is loaded and converted once and the taps are
- *       shifted descriptor windows of it (images that tile by 8x16, ragged images >= 32x32 with masked edge tiles,
- *       and small images whose tiles fit the machine in one wave).
- *   sg2_conv2d_select_impl resolves `impl` for a shape (0 = auto: halo > per-tap > fp32, `precise` picks the
- *   fp32-class flavour) and returns 1..5 (or SG2_ENOTSUP); pass the returned code to BOTH pack_weight and fwd.   */
+ *       4, 5 = tcgen05 "halo" kernels: the (8+2)x(16+2) patch of a tile is loaded once and the k*k taps are shifted descriptor
+ *       windows of it (input channels % 32 == 0, output channels % 32 == 0; images that tile by 8x16, ragged images >= 32x32
+ *       with masked edge tiles, and small images whose tiles fit the machine in one wave):
+ *   4 = "bf16x3": fp32 operands split into bf16 hi/lo pairs, the three products hi*hi + lo*hi + hi*lo accumulated in fp32
+ *       in TMEM (~5e-6 relative) -- data and weight gradients, which are linear in their operands;
+ *   5 = "fp32-class": operands split into fp16 big/small pairs carrying 22 mantissa bits (the residual scaled by 2^11), at
+ *       the full 16-bit MMA rate; the big*big accumulator is promoted into fp32 registers every few taps (the tensor core
+ *       truncates its accumulator per MMA): fp32-class results (~5e-7).  FORWARD convs use it: a relative input error eps
+ *       flips ~0.8*eps of the leaky-ReLU signs against the fp32 reference.
+ *   (2 and 3 were round 1's per-tap kernels; they no longer exist and are refused.)
+ *   sg2_conv2d_select_impl resolves `impl` for a shape (0 = auto: halo, else fp32; `precise` picks 5 over 4) and returns
+ *   1, 4 or 5 (or SG2_ENOTSUP); pass the returned code to BOTH pack_weight and fwd.   */
 int sg2_conv2d_select_impl(int n, int h, int w, int ci, int co, int k, int impl, int precise);
 int64_t sg2_conv2d_packed_size(int co, int ci, int k, int impl);   /* bytes */
 int sg2_conv2d_pack_weight(const float* w, void* packed, int co, int ci, int k,

@@ -35,7 +35,7 @@ for idx, (n, ci, co, k, hw) in enumerate(cases):
         ref1 = F.leaky_relu(F.conv2d(x * s[:, :, None, None], w * coef, padding=k // 2) * d[:, :, None, None] + b[None, :, None, None] + nz, 0.2)
         ref64 = F.leaky_relu(F.conv2d((x * s[:, :, None, None]).double(), (w * coef).double(), padding=k // 2) * d[:, :, None, None].double() + b[None, :, None, None].double() + nz.double(), 0.2)
         e32 = float((ref1.double() - ref64).abs().max() / ref64.abs().max())
-        for impl in ((2, 3, 4, 5) if hw % 16 == 0 else (2, 3)):
+        for impl in (4, 5):
             y0 = C._conv_raw(x, w, coef, False, impl=impl)
             y1 = C._conv_raw(x, w, coef, False, in_scale=s, out_scale=d, bias=b, noise=nz, slope=0.2, impl=impl)
             e64 = float((y1.double() - ref64).abs().max() / ref64.abs().max())
@@ -43,7 +43,7 @@ for idx, (n, ci, co, k, hw) in enumerate(cases):
         out.append(f'(torch fp32 vs fp64 {e32:.1e})')
         if ci in (32, 64) or ci % 128 == 0:
             ref2 = F.conv_transpose2d(gy, w * coef, padding=k // 2)
-            out.append(f'dgrad {err(C._conv_raw(gy, w, coef, True, impl=2), ref2):.1e}')
+            out.append(f'dgrad {err(C._conv_raw(gy, w, coef, True, impl=4), ref2):.1e}')
             if hw % 16 == 0:
                 out.append(f'dgrad-halo {err(C._conv_raw(gy, w, coef, True, impl=4), ref2):.1e}')
     if which in ('all', 'wgrad'):
@@ -51,10 +51,10 @@ for idx, (n, ci, co, k, hw) in enumerate(cases):
         wr = w.detach().clone().requires_grad_(True)
         yr = F.conv2d(xr, wr * coef, padding=k // 2)
         ref_w, = torch.autograd.grad(yr, wr, gy)
-        dw = C._wgrad_raw(x, gy, k, coef, impl=2)
+        dw = C._wgrad_raw(x, gy, k, coef, impl=4)
         yr2 = F.conv2d(xr * s[:, :, None, None], wr * coef, padding=k // 2) * d[:, :, None, None]
         ref_w2, = torch.autograd.grad(yr2, wr, gy)
-        dw2 = C._wgrad_raw(x, gy, k, coef, in_scale=s, out_scale=d, impl=2)
+        dw2 = C._wgrad_raw(x, gy, k, coef, in_scale=s, out_scale=d, impl=4)
         out.append(f'wgrad {err(dw, ref_w):.1e} scaled {err(dw2, ref_w2):.1e}')
     torch.cuda.synchronize()
     print('  '.join(out), flush=True)
