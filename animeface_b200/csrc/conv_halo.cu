@@ -78,6 +78,8 @@ struct Params {
     float alpha, gain;
     long long* trace;        // sg2_debug_trace buffer or null
     int promo_taps;          // PRECISE: taps accumulated in TMEM between two promotions (4 chained big*big MMAs per tap)
+    int bstages;             // weight stages in use (<= Cfg::BSTAGES)
+    int tma_store;           // 1x1 convolutions: staged TMA-store epilogue (see conv_halo_pl.cu)
 };
 
 // non-swizzled K-major descriptor: LBO between 16-byte K chunks, SBO between 8-row groups, 16 B between rows
@@ -86,15 +88,16 @@ __device__ __forceinline__ uint64_t interleave_desc(uint32_t addr, uint32_t lbo,
 }
 
 template <int BN, bool PRECISE>
-__global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
+__global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap ymap,
+                                                                                  const Params p) {
     using C = Cfg<BN, PRECISE>;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t slot_base = base;
     const uint32_t plane_base = slot_base + C::SLOTS * SLOT_BYTES;            // [buf][plane]
     const uint32_t b_base = plane_base + 4 * PLANE_PITCH;
-    constexpr int BSTAGES = C::BSTAGES;
-    const uint32_t bar_base = b_base + BSTAGES * C::BTILE;
+    const int BSTAGES = p.bstages;
+    const uint32_t bar_base = b_base + C::BSTAGES * C::BTILE;
     auto st_full = [&](int s) { return bar_base + 8u * s; };                  // 2
     auto st_empty = [&](int s) { return bar_base + 16u + 8u * s; };           // 2
     auto pl_full = [&](int b) { return bar_base + 32u + 8u * b; };            // 2
@@ -130,7 +133,7 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
             mbar_init(pl_full(s), 8); mbar_init(pl_empty(s), 1);
         }
         for (int s = 0; s < C::NACC; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), C::EPI_WARPS); }
-        for (int s = 0; s < BSTAGES; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        for (int s = 0; s < C::BSTAGES; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
         for (int s = 0; s < 2; ++s) mbar_init(d2_empty(s), C::EPI_WARPS);
         fence_barrier_init();
     }
@@ -150,9 +153,10 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
                 int x0, y0, b0, n0;
                 tile_coords(tile, x0, y0, b0, n0);
                 for (int kb = 0; kb < p.nkb; ++kb)
-                    for (int hb = 0; hb < C::BOXES; ++hb, ++bx) {
-                        const int s = bx % C::SLOTS;
-                        mbar_wait_t(st_empty(s), ((bx / C::SLOTS) & 1) ^ 1, tr, w0);
+                    for (int hb = 0; hb < C::BOXES; ++hb) {
+                        if (kb * C::KB + 32 * hb >= p.ci) continue;      // 32-channel tail: no box, no transform, no MMAs for it
+                        const int s = (bx++) % C::SLOTS;
+                        mbar_wait_t(st_empty(s), (((bx - 1) / C::SLOTS) & 1) ^ 1, tr, w0);
                         mbar_expect_tx(st_full(s), (uint32_t)PR * 128u);
                         tma_load_4d(slot_base + s * SLOT_BYTES, &xmap, st_full(s), kb * C::KB + 32 * hb, x0 - pad, y0 - pad, b0);
                     }
@@ -202,11 +206,13 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
                         const uint32_t arow = (uint32_t)(dy * PW + dx) * 16u;
                         const uint32_t a0 = plane(pbuf, 0) + arow, a1 = plane(pbuf, 1) + arow;
                         const uint32_t b0_ = b_base + s * C::BTILE;       // plane 0 rows, then plane 1 rows: 2*BN contiguous B rows
+                        const int kqn = min(4, (p.ci - kb * C::KB) >> 4);   // k16 steps that hold real channels (2 for a 32-channel tail)
                         if (C::D2X) {
                             const uint32_t d1 = tmem_d + (uint32_t)(abuf * 2 * BN), d2 = tmem_d + (uint32_t)(BN + tp * 2 * BN);
                             const bool adjacent = abuf == tp;     // D2 sits right behind this segment's D1
 #pragma unroll
                             for (int kq = 0; kq < 4; ++kq) {
+                                if (kq >= kqn) break;
                                 const uint64_t da0 = interleave_desc(a0 + 2 * kq * LBO, LBO, SBO), da1 = interleave_desc(a1 + 2 * kq * LBO, LBO, SBO);
                                 const uint64_t db = kmajor_desc(b0_ + kq * 32), db1 = kmajor_desc(b0_ + BN * 128 + kq * 32);
                                 const bool first_seg = seg_start && kq == 0, first_tile = f == 0 && kq == 0;
@@ -222,6 +228,7 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
                             const uint32_t d = tmem_d + (uint32_t)(abuf * C::ACC_COLS);
 #pragma unroll
                             for (int kq = 0; kq < 4; ++kq) {
+                                if (kq >= kqn) break;
                                 const uint64_t da0 = interleave_desc(a0 + 2 * kq * LBO, LBO, SBO), da1 = interleave_desc(a1 + 2 * kq * LBO, LBO, SBO);
                                 const uint64_t db = kmajor_desc(b0_ + kq * 32);
                                 mma_bf16(d, da0, db, idesc2, !(seg_start && kq == 0));        // [D1 | D2] += A0 * [B0 ; B1]
@@ -247,7 +254,8 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
                 const int pbuf = kbg & 1;
                 const uint32_t pl0 = plane(pbuf, 0), pl1 = plane(pbuf, 1);
                 bool waited = false;
-                for (int hb = 0; hb < C::BOXES; ++hb, ++bx) {
+                for (int hb = 0; hb < C::BOXES; ++hb) {
+                    if (kb * C::KB + 32 * hb >= p.ci) continue;
                     const int s = bx % C::SLOTS;
                     mbar_wait_t(st_full(s), (bx / C::SLOTS) & 1, tr, w0);
                     if (!waited) { mbar_wait_t(pl_empty(pbuf), ((kbg >> 1) & 1) ^ 1, tr, w1); waited = true; }
@@ -291,6 +299,7 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(st_empty(s));
+                    ++bx;
                 }
                 fence_proxy_async();
                 __syncwarp();
@@ -307,6 +316,9 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
         const int cstart = PRECISE ? (ew >> 2) * COLS : 0;
         const int nflat = p.nkb * taps;
         const int nseg = PRECISE ? (nflat + p.promo_taps - 1) / p.promo_taps : 1;
+        const uint32_t stg = b_base + (uint32_t)p.bstages * C::BTILE;         // TMA-store staging: [32-channel block][128 rows][128 B]
+        const uint32_t stg_row = stg + (uint32_t)er * 128u;
+        constexpr int EPI_THREADS = C::EPI_WARPS * 32;
         int sg = 0, tl = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
             int x0, y0, b0, n0;
@@ -328,6 +340,12 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
                     o[e] = val * p.gain;
                 }
                 const int cb = n0 + cstart + cbase;
+                if (p.tma_store) {
+                    const int ct = cstart + cbase, blk = ct >> 5, chunk = (ct & 31) >> 2;
+                    sts4(stg_row + (uint32_t)blk * (128u * 128u) + (uint32_t)((chunk ^ (er & 7)) << 4),
+                         __float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3]));
+                    return;
+                }
                 if (!inside) return;
                 if (p.ys[1] == 1) st4(yrow + cb, make_float4(o[0], o[1], o[2], o[3]));
                 else {
@@ -336,6 +354,11 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
                 }
             };
             const uint32_t lane_addr = tmem_d + ((uint32_t)(q4 * 32) << 16);
+            if (p.tma_store) {
+                // the previous tile's TMA stores must have READ the staging tile before it is overwritten
+                if (ew == 0 && lane == 0) bulk_wait_read_all();
+                named_bar_sync(1, EPI_THREADS);
+            }
             if (PRECISE) {
                 // every segment (the last one included) is promoted into fp32 registers -- acc += D1 + 2^-11 D2 -- and its
                 // TMEM buffer handed back at once; the epilogue then runs from registers while the MMA warp is already
@@ -437,7 +460,16 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
                 if (lane == 0) mbar_arrive(acc_empty(abuf));
                 ++sg;
             }
+            if (p.tma_store) {
+                fence_proxy_async();
+                named_bar_sync(1, EPI_THREADS);
+                if (ew == 0 && lane == 0) {
+                    for (int blk = 0; blk < BN / 32; ++blk) tma_store_4d(&ymap, stg + (uint32_t)blk * (128u * 128u), n0 + 32 * blk, x0, y0, b0);
+                    bulk_commit();
+                }
+            }
         }
+        if (p.tma_store && ew == 0 && lane == 0) bulk_wait_all();
         if (tr && ew == 0 && lane == 0) { trow[8] = w0; trow[9] = clock64() - t_begin; }
     }
     tc_fence_before();
@@ -492,7 +524,7 @@ __global__ void conv_pack_halo_kernel(const float* __restrict__ w, unsigned char
 static int pick_bn(int co) { return co % 128 == 0 ? 128 : (co % 64 == 0 ? 64 : (co % 32 == 0 ? 32 : 0)); }
 
 template <int BN, bool PRECISE>
-static int launch(const CUtensorMap& map, const Params& tp, dim3 grid, cudaStream_t st) {
+static int launch(const CUtensorMap& map, const CUtensorMap& ymap, Params& tp, dim3 grid, cudaStream_t st) {
     using C = Cfg<BN, PRECISE>;
     static bool configured = false;
     if (!configured) {
@@ -500,7 +532,12 @@ static int launch(const CUtensorMap& map, const Params& tp, dim3 grid, cudaStrea
         if (e != cudaSuccess) return fail(SG2_ELAUNCH, "conv_halo: cannot opt in to %d B of shared memory: %s", C::SMEM, cudaGetErrorString(e));
         configured = true;
     }
-    conv_halo_kernel<BN, PRECISE><<<grid, C::NTHREADS, C::SMEM, st>>>(map, tp);
+    tp.bstages = C::BSTAGES;
+    if (tp.tma_store) {
+        // a 1x1 convolution streams one weight tile per channel block: two stages suffice, the rest of the region stages the output
+        if ((C::BSTAGES - 2) * C::BTILE >= BN * 512) tp.bstages = 2; else tp.tma_store = 0;
+    }
+    conv_halo_kernel<BN, PRECISE><<<grid, C::NTHREADS, C::SMEM, st>>>(map, ymap, tp);
     return launched(PRECISE ? "conv_halo_fp16x3" : "conv_halo_bf16x3");
 }
 
@@ -580,15 +617,24 @@ int conv_fwd_halo(const ConvParams& p, int precise, cudaStream_t st) {
         if (promo_taps < 1 || promo_taps > 9) promo_taps = 5;
     }
     tp.promo_taps = promo_taps;
+    // TMA-store epilogue: 1x1 convolutions into a dense NHWC tensor (the skip convolutions of the discriminator blocks)
+    CUtensorMap ymap = map;
+    tp.tma_store = 0;
+    if (p.k == 1 && p.ys[1] == 1 && p.ys[3] == p.co && p.ys[2] == (long long)p.w * p.co && p.ys[0] == (long long)p.h * p.w * p.co &&
+        ((uintptr_t)p.y & 15) == 0) {
+        rc = tc::make_nhwc_map(&ymap, p.y, p.n, p.h, p.w, p.co, halo::TW, halo::TH, 1, "conv_fwd_halo(y)");
+        if (rc) return rc;
+        tp.tma_store = 1;
+    }
     dim3 grid((unsigned)std::min(tp.m_tiles * tp.n_tiles, num_sms()));
     if (precise) {
-        if (bn == 128) return halo::launch<128, true>(map, tp, grid, st);
-        if (bn == 64) return halo::launch<64, true>(map, tp, grid, st);
-        return halo::launch<32, true>(map, tp, grid, st);
+        if (bn == 128) return halo::launch<128, true>(map, ymap, tp, grid, st);
+        if (bn == 64) return halo::launch<64, true>(map, ymap, tp, grid, st);
+        return halo::launch<32, true>(map, ymap, tp, grid, st);
     }
-    if (bn == 128) return halo::launch<128, false>(map, tp, grid, st);
-    if (bn == 64) return halo::launch<64, false>(map, tp, grid, st);
-    return halo::launch<32, false>(map, tp, grid, st);
+    if (bn == 128) return halo::launch<128, false>(map, ymap, tp, grid, st);
+    if (bn == 64) return halo::launch<64, false>(map, ymap, tp, grid, st);
+    return halo::launch<32, false>(map, ymap, tp, grid, st);
 }
 
 }  // namespace sg2

@@ -44,10 +44,19 @@ struct Params {
     int act;
     float alpha, gain;
     int accumulate;          // y += result (the skip branch's data gradient lands on top of the main branch's)
+    int bstages;             // weight stages in use (<= Cfg::BSTAGES)
+    int tma_store;           // 1x1 convolutions: the epilogue stages the tile in shared memory and stores it with TMA (below)
 };
 
+// Epilogue stores.  A thread owns one pixel (accumulator row); stored straight from registers, one 16-byte store instruction of a
+// warp touches 32 different 128-byte lines -- for a 1x1 convolution (8 MMAs per tile) those 2 K store wavefronts per tile were the
+// whole kernel (role trace: MMA warp 60 % waiting for a free accumulator; 23 TF/s, 2.3 TB/s).  With tma_store the warps write
+// their rows into a SWIZZLE_128B staging tile (conflict-free: 8 lanes hit 8 different 16-byte chunks) and ONE elected thread
+// issues a TMA tensor store (or reduce-add, for `accumulate`) per 32-channel block; the staging tile lives in the weight stages
+// a 1x1 convolution does not need (it has one tap per channel block).
 template <int BN>
-__global__ void __launch_bounds__(NTHREADS, 1) conv_halo_pl_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
+__global__ void __launch_bounds__(NTHREADS, 1) conv_halo_pl_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap ymap,
+                                                                   const Params p) {
     using C = Cfg<BN>;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -113,8 +122,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_halo_pl_kernel(const __grid_
                 const int nt = tile / p.m_tiles;
                 const unsigned char* wsrc = p.wp + (size_t)nt * p.nkb * taps * C::BTILE;
                 for (int i = 0; i < p.nkb * taps; ++i, ++bt) {
-                    const int s = bt % C::BSTAGES;
-                    mbar_wait(b_empty(s), ((bt / C::BSTAGES) & 1) ^ 1);
+                    const int s = bt % p.bstages;
+                    mbar_wait(b_empty(s), ((bt / p.bstages) & 1) ^ 1);
                     mbar_expect_tx(b_full(s), C::BTILE);
                     bulk_load(b_base + s * C::BTILE, wsrc + (size_t)i * C::BTILE, C::BTILE, b_full(s));
                 }
@@ -135,13 +144,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_halo_pl_kernel(const __grid_
                     mbar_wait(pl_full(ps), (kbg / C::PSTAGES) & 1);
                     const uint32_t pl0 = plane_base + (uint32_t)(ps * 2) * PLANE_PITCH, pl1 = pl0 + PLANE_PITCH;
                     for (int t = 0, dy = 0, dx = 0; t < taps; ++t, ++bt, dx = (dx + 1 == p.k ? 0 : dx + 1), dy += (dx == 0)) {
-                        const int s = bt % C::BSTAGES;
-                        mbar_wait(b_full(s), (bt / C::BSTAGES) & 1);
+                        const int s = bt % p.bstages;
+                        mbar_wait(b_full(s), (bt / p.bstages) & 1);
                         tc_fence_after();
                         const uint32_t arow = (uint32_t)(dy * PW + dx) * 128u;
                         const uint32_t b0_ = b_base + s * C::BTILE;
+                        const int kqn = min(4, (p.ci - kb * 64) >> 4);      // 32-channel tail: the zero-filled half of the box is skipped
 #pragma unroll
                         for (int kq = 0; kq < 4; ++kq) {
+                            if (kq >= kqn) break;
                             const uint64_t da0 = kmajor_desc_sbo(pl0 + arow + kq * 32, SBO), da1 = kmajor_desc_sbo(pl1 + arow + kq * 32, SBO);
                             const uint64_t db = kmajor_desc(b0_ + kq * 32);
                             mma_bf16(d, da0, db, idesc2, !(kb == 0 && t == 0 && kq == 0));     // [hi*hi | hi*lo] += A_hi * [B_hi ; B_lo]
@@ -158,6 +169,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_halo_pl_kernel(const __grid_
         // ================= epilogue warps =================
         const int q4 = warp & 3;
         const int er = q4 * 32 + lane;                    // accumulator row = pixel (y*8 + x)
+        const uint32_t stg = b_base + (uint32_t)p.bstages * C::BTILE;         // staging tile: [32-channel block][128 rows][128 B]
+        const uint32_t stg_row = stg + (uint32_t)er * 128u;
         int sg = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++sg) {
             int x0, y0, b0, n0;
@@ -171,6 +184,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_halo_pl_kernel(const __grid_
             const int abuf = sg % C::NACC;
             mbar_wait(acc_full(abuf), (sg / C::NACC) & 1);
             tc_fence_after();
+            if (p.tma_store) {
+                // the previous tile's TMA stores must have READ the staging tile before it is overwritten
+                if (warp == 2 && lane == 0) bulk_wait_read_all();
+                named_bar_sync(1, 128);
+            }
 #pragma unroll 1
             for (int c = 0; c < BN / 16; ++c) {
                 uint32_t v[16], v2[16];
@@ -192,7 +210,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_halo_pl_kernel(const __grid_
                         if (p.act == 3) val = val > 0.f ? val : val * p.alpha;
                         o[e] = val * p.gain;
                     }
-                    if (inside) {
+                    if (p.tma_store) {
+                        const int blk = cbase >> 5, chunk = (cbase & 31) >> 2;
+                        sts4(stg_row + (uint32_t)blk * (128u * 128u) + (uint32_t)((chunk ^ (er & 7)) << 4),
+                             __float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3]));
+                    } else if (inside) {
                         const int cb = n0 + cbase;
                         if (p.ys[1] == 1) {
                             if (p.accumulate) { const float4 t = *reinterpret_cast<const float4*>(yrow + cb); o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w; }
@@ -210,7 +232,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_halo_pl_kernel(const __grid_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty(abuf));
+            if (p.tma_store) {
+                fence_proxy_async();                      // the staging writes become visible to the async proxy (TMA)
+                named_bar_sync(1, 128);
+                if (warp == 2 && lane == 0) {
+                    for (int blk = 0; blk < BN / 32; ++blk) {
+                        if (p.accumulate) tma_reduce_add_4d(&ymap, stg + (uint32_t)blk * (128u * 128u), n0 + 32 * blk, x0, y0, b0);
+                        else tma_store_4d(&ymap, stg + (uint32_t)blk * (128u * 128u), n0 + 32 * blk, x0, y0, b0);
+                    }
+                    bulk_commit();
+                }
+            }
         }
+        if (p.tma_store && warp == 2 && lane == 0) bulk_wait_all();
     }
     tc_fence_before();
     __syncthreads();
@@ -224,7 +258,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_halo_pl_kernel(const __grid_
 static int pick_bn(int co) { return co % 128 == 0 ? 128 : (co % 64 == 0 ? 64 : (co % 32 == 0 ? 32 : 0)); }
 
 template <int BN>
-static int launch(const CUtensorMap& map, const Params& tp, dim3 grid, cudaStream_t st) {
+static int launch(const CUtensorMap& map, const CUtensorMap& ymap, Params& tp, dim3 grid, cudaStream_t st) {
     using C = Cfg<BN>;
     static bool configured = false;
     if (!configured) {
@@ -232,7 +266,12 @@ static int launch(const CUtensorMap& map, const Params& tp, dim3 grid, cudaStrea
         if (e != cudaSuccess) return fail(SG2_ELAUNCH, "conv_halo_pl: cannot opt in to %d B of shared memory: %s", C::SMEM, cudaGetErrorString(e));
         configured = true;
     }
-    conv_halo_pl_kernel<BN><<<grid, NTHREADS, C::SMEM, st>>>(map, tp);
+    tp.bstages = C::BSTAGES;
+    if (tp.tma_store) {
+        // a 1x1 convolution streams one weight tile per channel block: two stages are plenty, the rest of the region is the staging tile
+        if ((C::BSTAGES - 2) * C::BTILE >= BN * 512) tp.bstages = 2; else tp.tma_store = 0;
+    }
+    conv_halo_pl_kernel<BN><<<grid, NTHREADS, C::SMEM, st>>>(map, ymap, tp);
     return launched("conv_halo_pl");
 }
 
@@ -264,10 +303,19 @@ int conv_fwd_halo_pl(const void* x_planes, const ConvParams& p, int accumulate, 
     tp.n_tiles = p.co / bn;
     tp.nkb = (p.ci + 63) / 64;
     tp.act = p.act; tp.alpha = p.alpha; tp.gain = p.gain; tp.accumulate = accumulate;
+    // TMA-store epilogue: 1x1 convolutions into a dense NHWC tensor
+    CUtensorMap ymap = map;
+    tp.tma_store = 0;
+    if (p.k == 1 && p.ys[1] == 1 && p.ys[3] == p.co && p.ys[2] == (long long)p.w * p.co && p.ys[0] == (long long)p.h * p.w * p.co &&
+        ((uintptr_t)p.y & 15) == 0) {
+        rc = tc::make_nhwc_map(&ymap, p.y, p.n, p.h, p.w, p.co, halopl::TW, halopl::TH, 1, "conv_fwd_halo_pl(y)");
+        if (rc) return rc;
+        tp.tma_store = 1;
+    }
     dim3 grid((unsigned)std::min(tp.m_tiles * tp.n_tiles, num_sms()));
-    if (bn == 128) return halopl::launch<128>(map, tp, grid, st);
-    if (bn == 64) return halopl::launch<64>(map, tp, grid, st);
-    return halopl::launch<32>(map, tp, grid, st);
+    if (bn == 128) return halopl::launch<128>(map, ymap, tp, grid, st);
+    if (bn == 64) return halopl::launch<64>(map, ymap, tp, grid, st);
+    return halopl::launch<32>(map, ymap, tp, grid, st);
 }
 
 }  // namespace sg2

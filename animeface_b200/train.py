@@ -136,6 +136,12 @@ class Trainer:
             self.augment = functools.partial(DiffAugment, policy=cfg.policy)
         self.batches_done = 0
         self._d_params = list(D.parameters())
+        # data parallel: the discriminator's gradient exchange + Adam step run on a side stream while the main stream already
+        # computes the generator forward of the G phase (which does not read D); the main stream joins before D is used again.
+        # Inside a captured step the fork / join become graph dependencies.
+        self._side = None
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and next(D.parameters()).is_cuda:
+            self._side = torch.cuda.Stream(device=next(D.parameters()).device)
         # running mean of the path-length penalty (utils.py:44, 100-103), on the device so the step never syncs
         self.pl_mean = torch.zeros((), dtype=torch.float32, device=next(G.parameters()).device)
 
@@ -175,7 +181,16 @@ class Trainer:
             if self.ada is not None:
                 self.ada.update_p(prob[:B].detach())          # overfitting heuristic on D(real_aug); device-side, no sync
         D_loss.backward()
-        self.opt_d.step()
+        d_done = None
+        if self._side is not None:
+            fork = torch.cuda.current_stream().record_event()
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(fork)
+                self.opt_d.step()
+                d_done = self._side.record_event()
+        else:
+            self.opt_d.step()
+        join_d = (lambda: torch.cuda.current_stream().wait_event(d_done)) if d_done is not None else (lambda: None)
         # ---- generator phase (utils.py:88-113)
         z = rng.randn(B, cfg.style_dim, device=dev)
         for p in self._d_params:
@@ -186,6 +201,7 @@ class Trainer:
                 # value, its augmentation draws are still consumed in the reference's order.
                 with any_order_modconv():
                     fake, style = G(z)
+                join_d()
                 with torch.no_grad():
                     self.augment(fake)
                 pl = pl_penalty(style, fake, self.pl_mean)
@@ -194,6 +210,7 @@ class Trainer:
                 self.pl_mean.copy_(update_pl_mean(self.pl_mean, pl.detach()))
             else:
                 fake, _ = G(z)
+                join_d()                                    # D's updated weights are needed from here on
                 fake_prob = D(self.augment(fake))
                 G_loss = self.loss.g_loss(fake_prob)
                 G_loss.backward()

@@ -28,15 +28,18 @@ def cl(*shape):
 
 
 def run(name):
+    k = 3
+    if name.endswith('k1'):
+        name, k = name[:-2], 1
     kind = name.rstrip('0123456789x')
     ci, co, r = SHAPES[name[len(kind):]]
-    w = torch.randn(co, ci, 3, 3, device=DEV)
+    w = torch.randn(co, ci, k, k, device=DEV)
     if kind == 'fwd':
         x = cl(B, ci, r, r); fn = lambda: C._conv_raw(x, w, 0.1, False)
     elif kind == 'dgrad':
         x = cl(B, co, r, r); fn = lambda: C._conv_raw(x, w, 0.1, True)
     else:
-        x, gy = cl(B, ci, r, r), cl(B, co, r, r); fn = lambda: C._wgrad_raw(x, gy, 3, 0.1)
+        x, gy = cl(B, ci, r, r), cl(B, co, r, r); fn = lambda: C._wgrad_raw(x, gy, k, 0.1)
     fn(); fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
