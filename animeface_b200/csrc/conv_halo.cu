@@ -25,6 +25,9 @@
 // Warp roles: 0 patch TMA, 1 MMA (+TMEM alloc), 2..9 transform, 10.. epilogue/promotion, last = weight TMA.
 #include <stdlib.h>
 #include "tc_common.cuh"
+#ifndef SG2_TRACE_EPI
+#define SG2_TRACE_EPI 0      // 1: the epilogue warps also time their phases (slots 13-15 of sg2_debug_trace); costs registers
+#endif
 #include "conv.h"
 
 namespace sg2 {
@@ -80,7 +83,10 @@ struct Params {
     int promo_taps;          // PRECISE: taps accumulated in TMEM between two promotions (4 chained big*big MMAs per tap)
     int bstages;             // weight stages in use (<= Cfg::BSTAGES)
     int tma_store;           // 1x1 convolutions: staged TMA-store epilogue (see conv_halo_pl.cu)
+    int tx_shift, ty_shift;  // log2(tiles_x), log2(tiles_y) when both are powers of two, else -1
 };
+
+template <int M> struct Mode { static constexpr int value = M; };      // compile-time store mode of the epilogue
 
 // non-swizzled K-major descriptor: LBO between 16-byte K chunks, SBO between 8-row groups, 16 B between rows
 __device__ __forceinline__ uint64_t interleave_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
@@ -112,7 +118,7 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool tr = p.trace != nullptr;
-    long long* trow = p.trace + (size_t)blockIdx.x * 16;
+    long long* trow = p.trace + (size_t)blockIdx.x * 32;
     const long long t_begin = tr ? clock64() : 0;
     long long w0 = 0, w1 = 0, w2 = 0;            // wait-cycle accumulators of this thread's role
     const int pad = p.k >> 1, taps = p.k * p.k;
@@ -120,10 +126,17 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
     const uint32_t LBO = (uint32_t)PR * 16u, SBO = (uint32_t)PW * 16u;
     const int total_tiles = p.m_tiles * p.n_tiles;
     auto tile_coords = [&](int tile, int& x0, int& y0, int& b0, int& n0) {
-        const int nt = tile / p.m_tiles, mt = tile % p.m_tiles;
-        x0 = (mt % p.tiles_x) * TW;
-        y0 = ((mt / p.tiles_x) % p.tiles_y) * TH;
-        b0 = mt / (p.tiles_x * p.tiles_y);
+        int nt = 0, mt = tile;                             // n_tiles is 1..4: no division
+        while (mt >= p.m_tiles) { mt -= p.m_tiles; ++nt; }
+        if (p.tx_shift >= 0) {                             // power-of-two tile grid (every layer of the 256^2 path): shifts and masks
+            x0 = (mt & (p.tiles_x - 1)) * TW;
+            y0 = ((mt >> p.tx_shift) & (p.tiles_y - 1)) * TH;
+            b0 = mt >> (p.tx_shift + p.ty_shift);
+        } else {
+            x0 = (mt % p.tiles_x) * TW;
+            y0 = ((mt / p.tiles_x) % p.tiles_y) * TH;
+            b0 = mt / (p.tiles_x * p.tiles_y);
+        }
         n0 = nt * BN;
     };
 
@@ -166,82 +179,100 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
     } else if (warp == C::BWARP) {
         // ================= weight producer: one pre-packed tile per (tile, channel block, tap) =================
         if (elect_one()) {
-            int bt = 0;
+            int s = 0;
+            uint32_t sph = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int nt = tile / p.m_tiles;
+                int nt = 0;
+                for (int mt = tile; mt >= p.m_tiles; mt -= p.m_tiles) ++nt;
                 const unsigned char* wsrc = p.wp + (size_t)nt * p.nkb * taps * C::BTILE;
-                for (int i = 0; i < p.nkb * taps; ++i, ++bt) {
-                    const int s = bt % BSTAGES;
-                    mbar_wait_t(b_empty(s), ((bt / BSTAGES) & 1) ^ 1, tr, w0);
+                for (int i = 0; i < p.nkb * taps; ++i) {
+                    mbar_wait_t(b_empty(s), sph ^ 1, tr, w0);
                     mbar_expect_tx(b_full(s), C::BTILE);
                     bulk_load(b_base + s * C::BTILE, wsrc + (size_t)i * C::BTILE, C::BTILE, b_full(s));
+                    if (++s == BSTAGES) { s = 0; sph ^= 1; }
                 }
             }
             if (tr) trow[10] = w0;
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
+        // One thread, and it paces the low-channel layers: the loop below is kept free of divisions and 64-bit descriptor
+        // arithmetic (descriptor low words advance by adds, stage / buffer indices by wrap-around counters).
         if (elect_one()) {
             constexpr uint32_t idesc = PRECISE ? idesc_f16(BM, BN) : idesc_bf16(BM, BN);              // N = BN
             constexpr uint32_t idesc2 = PRECISE ? idesc_f16(BM, 2 * BN) : idesc_bf16(BM, 2 * BN);     // N = 2 BN (both weight planes)
-            int bt = 0, kbg = 0, sg = 0, tcount = 0;      // global weight-tile / channel-block / accumulator-segment / tile counters
+            const uint32_t a_hi = (SBO >> 4) | (1u << 14);                        // A: interleaved K-major, version bit 46
+            const uint32_t a_lo_f = (LBO >> 4) << 16;
+            const uint32_t kstep = (2u * LBO) >> 4;                               // one k16 step = two 16-byte K chunks
+            constexpr uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);     // B: K-major SWIZZLE_128B, SBO 1024
+            constexpr uint32_t b_lo_f = 1u << 16;
+            const uint32_t nstages = (uint32_t)BSTAGES, promo = (uint32_t)p.promo_taps;
+            const uint32_t kdim = (uint32_t)p.k, row_wrap = (uint32_t)(PW - p.k);
+            const uint32_t nflat = (uint32_t)(p.nkb * taps);
+            uint32_t s = 0, sph = 0, abuf = 0, aph = 0, kbg = 0, tcount = 0;      // weight stage / accumulator buffer (+ phases), block / tile counters
+            long long t_issue = 0, t_commit = 0;          // trace: cycles issuing MMAs / commits
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-                int f = 0, fseg = 0;                      // flat (kb, tap) index inside the tile / inside the accumulator segment
-                const int nflat = p.nkb * taps;
-                const int tp = tcount & 1;                // D2X: which D2 buffer this tile accumulates its cross terms in
-                if (C::D2X) mbar_wait_t(d2_empty(tp), ((tcount >> 1) & 1) ^ 1, tr, w2);
-                for (int kb = 0; kb < p.nkb; ++kb, ++kbg) {
-                    const int pbuf = kbg & 1;
+                uint32_t f = 0, fseg = 0;                 // flat (kb, tap) index inside the tile / inside the accumulator segment
+                const uint32_t tp = tcount & 1;           // D2X: which D2 buffer this tile accumulates its cross terms in
+                if (C::D2X) { mbar_wait_t(d2_empty(tp), ((tcount >> 1) & 1) ^ 1, tr, w2); tc_fence_after(); }
+                int ci_left = p.ci;
+                for (int kb = 0; kb < p.nkb; ++kb, ++kbg, ci_left -= C::KB) {
+                    const uint32_t pbuf = kbg & 1;
                     mbar_wait_t(pl_full(pbuf), (kbg >> 1) & 1, tr, w0);
-                    for (int t = 0, dy = 0, dx = 0; t < taps; ++t, ++bt, ++f, dx = (dx + 1 == p.k ? 0 : dx + 1), dy += (dx == 0)) {
-                        // accumulator segment: PRECISE -> every 2 taps, else the whole tile
+                    const uint32_t a0_base = ((plane(pbuf, 0) & 0x3FFFFu) >> 4) | a_lo_f, a1_base = a0_base + (PLANE_PITCH >> 4);
+                    const int kqn = min(4, ci_left >> 4);           // k16 steps that hold real channels (2 for a 32-channel tail)
+                    uint32_t arow = 0, dx = 0;                      // (dy * PW + dx): the tap's first patch row
+                    for (int t = 0; t < taps; ++t, ++f) {
+                        // accumulator segment: PRECISE -> every promo_taps taps, else the whole tile
                         const bool seg_start = PRECISE ? (fseg == 0) : (f == 0);
-                        const bool seg_end = PRECISE ? (fseg == p.promo_taps - 1 || f == nflat - 1) : (f == nflat - 1);
+                        const bool seg_end = PRECISE ? (fseg == promo - 1 || f == nflat - 1) : (f == nflat - 1);
                         fseg = seg_end ? 0 : fseg + 1;
-                        const int abuf = sg % C::NACC;
-                        if (seg_start) mbar_wait_t(acc_empty(abuf), ((sg / C::NACC) & 1) ^ 1, tr, w2);
-                        const int s = bt % BSTAGES;
-                        mbar_wait_t(b_full(s), (bt / BSTAGES) & 1, tr, w1);
-                        tc_fence_after();
-                        const uint32_t arow = (uint32_t)(dy * PW + dx) * 16u;
-                        const uint32_t a0 = plane(pbuf, 0) + arow, a1 = plane(pbuf, 1) + arow;
-                        const uint32_t b0_ = b_base + s * C::BTILE;       // plane 0 rows, then plane 1 rows: 2*BN contiguous B rows
-                        const int kqn = min(4, (p.ci - kb * C::KB) >> 4);   // k16 steps that hold real channels (2 for a 32-channel tail)
+                        if (seg_start) { mbar_wait_t(acc_empty(abuf), aph ^ 1, tr, w2); tc_fence_after(); }
+                        mbar_wait_t(b_full(s), sph, tr, w1);
+                        const long long ti0 = tr ? clock64() : 0;
+                        const uint32_t a0 = a0_base + arow, a1 = a1_base + arow;
+                        const uint32_t b0_ = (((b_base + s * C::BTILE) & 0x3FFFFu) >> 4) | b_lo_f;   // plane 0 rows, then plane 1 rows: 2*BN contiguous B rows
                         if (C::D2X) {
                             const uint32_t d1 = tmem_d + (uint32_t)(abuf * 2 * BN), d2 = tmem_d + (uint32_t)(BN + tp * 2 * BN);
                             const bool adjacent = abuf == tp;     // D2 sits right behind this segment's D1
 #pragma unroll
                             for (int kq = 0; kq < 4; ++kq) {
                                 if (kq >= kqn) break;
-                                const uint64_t da0 = interleave_desc(a0 + 2 * kq * LBO, LBO, SBO), da1 = interleave_desc(a1 + 2 * kq * LBO, LBO, SBO);
-                                const uint64_t db = kmajor_desc(b0_ + kq * 32), db1 = kmajor_desc(b0_ + BN * 128 + kq * 32);
+                                const uint32_t da0 = a0 + kq * kstep, da1 = a1 + kq * kstep, db = b0_ + kq * 2, db1 = db + (BN * 128 >> 4);
                                 const bool first_seg = seg_start && kq == 0, first_tile = f == 0 && kq == 0;
                                 if (adjacent && !first_seg) {
-                                    mma_bf16(d1, da0, db, idesc2, 1);                     // [D1 | D2] += A0 * [B0 ; B1]
+                                    mma_f16_words(d1, da0, a_hi, db, b_hi, idesc2, 1);             // [D1 | D2] += A0 * [B0 ; B1]
                                 } else {
-                                    mma_bf16(d1, da0, db, idesc, !first_seg);             // D1 (restarted at a segment start) += A0 * B0
-                                    mma_bf16(d2, da0, db1, idesc, !first_tile);           // D2 (restarted at a tile start)   += A0 * B1
+                                    mma_f16_words(d1, da0, a_hi, db, b_hi, idesc, !first_seg);     // D1 (restarted at a segment start) += A0 * B0
+                                    mma_f16_words(d2, da0, a_hi, db1, b_hi, idesc, !first_tile);   // D2 (restarted at a tile start)   += A0 * B1
                                 }
-                                mma_bf16(d2, da1, db, idesc, 1);                          // D2 += A1 * B0
+                                mma_f16_words(d2, da1, a_hi, db, b_hi, idesc, 1);                  // D2 += A1 * B0
                             }
                         } else {
                             const uint32_t d = tmem_d + (uint32_t)(abuf * C::ACC_COLS);
 #pragma unroll
                             for (int kq = 0; kq < 4; ++kq) {
                                 if (kq >= kqn) break;
-                                const uint64_t da0 = interleave_desc(a0 + 2 * kq * LBO, LBO, SBO), da1 = interleave_desc(a1 + 2 * kq * LBO, LBO, SBO);
-                                const uint64_t db = kmajor_desc(b0_ + kq * 32);
-                                mma_bf16(d, da0, db, idesc2, !(seg_start && kq == 0));        // [D1 | D2] += A0 * [B0 ; B1]
-                                mma_bf16(d + BN, da1, db, idesc, 1);                          //       D2  += A1 * B0
+                                const uint32_t da0 = a0 + kq * kstep, da1 = a1 + kq * kstep, db = b0_ + kq * 2;
+                                mma_f16_words(d, da0, a_hi, db, b_hi, idesc2, !(seg_start && kq == 0));   // [D1 | D2] += A0 * [B0 ; B1]
+                                mma_f16_words(d + BN, da1, a_hi, db, b_hi, idesc, 1);                     //       D2  += A1 * B0
                             }
                         }
+                        const long long ti1 = tr ? clock64() : 0;
                         mma_commit(b_empty(s));
-                        if (seg_end) { mma_commit(acc_full(abuf)); ++sg; }
+                        if (++s == nstages) { s = 0; sph ^= 1; }
+                        if (seg_end) {
+                            mma_commit(acc_full(abuf));
+                            if (++abuf == C::NACC) { abuf = 0; aph ^= 1; }
+                        }
+                        ++arow;
+                        if (++dx == kdim) { dx = 0; arow += row_wrap; }
+                        if (tr) { t_issue += ti1 - ti0; t_commit += clock64() - ti1; }
                     }
                     mma_commit(pl_empty(pbuf));
                 }
             }
-            if (tr) { trow[4] = w0; trow[5] = w1; trow[6] = w2; trow[7] = clock64() - t_begin; }
+            if (tr) { trow[4] = w0; trow[5] = w1; trow[6] = w2; trow[7] = clock64() - t_begin; trow[16] = t_issue; trow[17] = t_commit; }
         }
     } else if (warp < 10) {
         // ================= transform: fp32 box -> split planes (non-swizzled K-major) =================
@@ -317,9 +348,15 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
         const int nflat = p.nkb * taps;
         const int nseg = PRECISE ? (nflat + p.promo_taps - 1) / p.promo_taps : 1;
         const uint32_t stg = b_base + (uint32_t)p.bstages * C::BTILE;         // TMA-store staging: [32-channel block][128 rows][128 B]
-        const uint32_t stg_row = stg + (uint32_t)er * 128u;
+        const uint32_t stg_thr = stg + (uint32_t)er * 128u + (uint32_t)(cstart >> 5) * (128u * 128u);
+        const uint32_t stg_x = (uint32_t)(((cstart & 31) >> 2) ^ (er & 7));
         constexpr int EPI_THREADS = C::EPI_WARPS * 32;
+        const float alpha_eff = p.act == 3 ? p.alpha : 1.f, gain = p.gain;
+        const int smode = p.tma_store ? 0 : (p.ys[1] == 1 ? 1 : 2);
         int sg = 0, tl = 0;
+#if SG2_TRACE_EPI
+        long long t_promo = 0, t_fin = 0, t_stage = 0;     // trace: cycles in promotion / finish+store / staging hand-over
+#endif
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
             int x0, y0, b0, n0;
             tile_coords(tile, x0, y0, b0, n0);
@@ -330,35 +367,48 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
             float* yrow = p.y + (long long)b0 * p.ys[0] + (long long)ey * p.ys[2] + (long long)ex * p.ys[3];
             const float* osc = p.out_scale ? p.out_scale + (long long)b0 * p.co + n0 + cstart : nullptr;
             const float* bsp = p.bias ? p.bias + n0 + cstart : nullptr;
-            auto finish4 = [&](float (&o)[4], int cbase) {          // out_scale, bias, noise, activation, gain on 4 channels
-                if (osc) { const float4 t = ldg4(osc + cbase); o[0] *= t.x; o[1] *= t.y; o[2] *= t.z; o[3] *= t.w; }
-                if (bsp) { const float4 t = ldg4(bsp + cbase); o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w; }
+            float* ydense = yrow + n0 + cstart;                                  // mode 1: this thread's first channel of its pixel
+            // out_scale, bias, noise, activation, gain on 4 channels, then the store.  MODE (compile time; chosen once per kernel):
+            // 0 = swizzled staging tile for the TMA store, 1 = dense NHWC (16-byte stores), 2 = any strides.
+            auto finish4 = [&](auto mode, float (&o)[4], int cbase) {
+                constexpr int MODE = decltype(mode)::value;
+                const float4 sc = osc ? ldg4(osc + cbase) : make_float4(1.f, 1.f, 1.f, 1.f);
+                const float4 bi = bsp ? ldg4(bsp + cbase) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, biv[4] = {bi.x, bi.y, bi.z, bi.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    float val = o[e] + nz;
-                    if (p.act == 3) val = val > 0.f ? val : val * p.alpha;
-                    o[e] = val * p.gain;
+                    const float val = fmaf(o[e], scv[e], biv[e]) + nz;
+                    o[e] = (val > 0.f ? val : val * alpha_eff) * gain;
                 }
-                const int cb = n0 + cstart + cbase;
-                if (p.tma_store) {
-                    const int ct = cstart + cbase, blk = ct >> 5, chunk = (ct & 31) >> 2;
-                    sts4(stg_row + (uint32_t)blk * (128u * 128u) + (uint32_t)((chunk ^ (er & 7)) << 4),
+                if (MODE == 0) {
+                    // staging address: [32-channel block][row][16-byte chunk ^ (row & 7)]; cstart is a multiple of 16, cbase < COLS
+                    sts4(stg_thr + (uint32_t)(cbase >> 5) * (128u * 128u) + ((stg_x ^ (uint32_t)((cbase & 31) >> 2)) << 4),
                          __float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3]));
-                    return;
-                }
-                if (!inside) return;
-                if (p.ys[1] == 1) st4(yrow + cb, make_float4(o[0], o[1], o[2], o[3]));
-                else {
+                } else if (MODE == 1) {
+                    if (inside) st4(ydense + cbase, make_float4(o[0], o[1], o[2], o[3]));
+                } else {
+                    if (inside) {
+                        const int cb = n0 + cstart + cbase;
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) yrow[(long long)(cb + e) * p.ys[1]] = o[e];
+                        for (int e = 0; e < 4; ++e) yrow[(long long)(cb + e) * p.ys[1]] = o[e];
+                    }
                 }
             };
             const uint32_t lane_addr = tmem_d + ((uint32_t)(q4 * 32) << 16);
+#if SG2_TRACE_EPI
+            long long tq = tr ? clock64() : 0;
+#endif
             if (p.tma_store) {
                 // the previous tile's TMA stores must have READ the staging tile before it is overwritten
                 if (ew == 0 && lane == 0) bulk_wait_read_all();
                 named_bar_sync(1, EPI_THREADS);
+#if SG2_TRACE_EPI
+                if (tr) { const long long t = clock64(); t_stage += t - tq; tq = t; }
+#endif
             }
+#if SG2_TRACE_EPI
+            const long long w_before = w0;
+#endif
             if (PRECISE) {
                 // every segment (the last one included) is promoted into fp32 registers -- acc += D1 + 2^-11 D2 -- and its
                 // TMEM buffer handed back at once; the epilogue then runs from registers while the MMA warp is already
@@ -430,11 +480,20 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
                     __syncwarp();
                     if (lane == 0) mbar_arrive(d2_empty(tp));
                 }
+#if SG2_TRACE_EPI
+                if (tr) { const long long t = clock64(); t_promo += t - tq - (w0 - w_before); tq = t; }
+#endif
+                auto finish_all = [&](auto mode) {
 #pragma unroll
-                for (int j = 0; j < COLS; j += 4) {
-                    float o[4] = {racc[j], racc[j + 1], racc[j + 2], racc[j + 3]};
-                    finish4(o, j);
-                }
+                    for (int j = 0; j < COLS; j += 4) {
+                        float o[4] = {racc[j], racc[j + 1], racc[j + 2], racc[j + 3]};
+                        finish4(mode, o, j);
+                    }
+                };
+                if (smode == 0) finish_all(Mode<0>{}); else if (smode == 1) finish_all(Mode<1>{}); else finish_all(Mode<2>{});
+#if SG2_TRACE_EPI
+                if (tr) { const long long t = clock64(); t_fin += t - tq; tq = t; }
+#endif
             } else {
                 // one segment per tile: read both halves (hi*hi | hi*lo + lo*hi), add, finish, store, hand the buffer back
                 const int abuf = sg % C::NACC;
@@ -452,7 +511,8 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
                     for (int j = 0; j < 16; j += 4) {
                         float o[4] = {__uint_as_float(v[j]) + __uint_as_float(v2[j]), __uint_as_float(v[j + 1]) + __uint_as_float(v2[j + 1]),
                                       __uint_as_float(v[j + 2]) + __uint_as_float(v2[j + 2]), __uint_as_float(v[j + 3]) + __uint_as_float(v2[j + 3])};
-                        finish4(o, c * 16 + j);
+                        if (smode == 0) finish4(Mode<0>{}, o, c * 16 + j); else if (smode == 1) finish4(Mode<1>{}, o, c * 16 + j);
+                        else finish4(Mode<2>{}, o, c * 16 + j);
                     }
                 }
                 tc_fence_before();
@@ -467,10 +527,18 @@ __global__ void __launch_bounds__(Cfg<BN, PRECISE>::NTHREADS, 1) conv_halo_kerne
                     for (int blk = 0; blk < BN / 32; ++blk) tma_store_4d(&ymap, stg + (uint32_t)blk * (128u * 128u), n0 + 32 * blk, x0, y0, b0);
                     bulk_commit();
                 }
+#if SG2_TRACE_EPI
+                if (tr) t_stage += clock64() - tq;
+#endif
             }
         }
         if (p.tma_store && ew == 0 && lane == 0) bulk_wait_all();
-        if (tr && ew == 0 && lane == 0) { trow[8] = w0; trow[9] = clock64() - t_begin; }
+        if (tr && ew == 0 && lane == 0) {
+            trow[8] = w0; trow[9] = clock64() - t_begin;
+#if SG2_TRACE_EPI
+            trow[13] = t_promo; trow[14] = t_fin; trow[15] = t_stage;
+#endif
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -597,6 +665,9 @@ int conv_fwd_halo(const ConvParams& p, int precise, cudaStream_t st) {
     tp.n = p.n; tp.h = p.h; tp.w = p.w; tp.ci = p.ci; tp.co = p.co; tp.k = p.k;
     tp.tiles_x = (p.w + halo::TW - 1) / halo::TW; tp.tiles_y = (p.h + halo::TH - 1) / halo::TH;
     tp.m_tiles = tp.tiles_x * tp.tiles_y * p.n;
+    auto log2_exact = [](int v) { int l = 0; while ((1 << l) < v) ++l; return (1 << l) == v ? l : -1; };
+    tp.tx_shift = log2_exact(tp.tiles_x); tp.ty_shift = log2_exact(tp.tiles_y);
+    if (tp.tx_shift < 0 || tp.ty_shift < 0) tp.tx_shift = tp.ty_shift = -1;
     const int bn = halo::pick_bn(p.co);
     tp.n_tiles = p.co / bn;
     tp.nkb = (p.ci + 63) / 64;

@@ -64,6 +64,10 @@ def main():
             elif name in ('prep64', 'split64'):
                 gy, y = cl(B, 64, 256, 256), cl(B, 64, 256, 256)
                 twice((lambda: C._bwd_prep_planes(gy, y, 0.2)) if name == 'prep64' else (lambda: C._split_planes(gy)))
+            elif name == 'fwdk1':
+                x, w1 = cl(B, 32, 256, 256), torch.randn(64, 32, 1, 1, device=DEV)
+                bias = torch.randn(64, device=DEV)
+                twice(lambda: C._conv_raw(x, w1, 0.1, False, bias=bias))
             else:
                 kind = name.rstrip('0123456789x')
                 ci, co, r = SHAPES[name[len(kind):]]
