@@ -10,7 +10,7 @@
 // addresses, so any row-shifted start and any group stride read correctly (scripts/exp_umma_shift.cu,
 // profiles/r2a_umma_shift.txt).  MMA scheme, weight tiles, accumulators and epilogue are those of conv_halo.cu:
 //   per (tap, k16): [hi*hi | hi*lo] += A_hi x [B_hi ; B_lo] (N = 2 BN),  upper half += A_lo x B_hi;  result = lower + upper.
-// Warp roles: 0 patch TMA, 1 MMA (+TMEM alloc), 2..5 epilogue, 6 weight TMA.
+// Warp roles: 0 patch TMA, 1 MMA (+TMEM alloc), 2..9 epilogue, 10 weight TMA.
 #include <cuda_bf16.h>
 #include "tc_common.cuh"
 #include "conv.h"
@@ -21,17 +21,23 @@ using namespace tc;
 
 constexpr int TW = 8, TH = 16, BM = 128;
 constexpr int PLANE_PITCH = 23 * 1024;                  // 180 patch rows x 128 B = 23040, 1024-aligned pitch
-constexpr int NTHREADS = 7 * 32;
+constexpr int EPI_WARPS = 8;                           // two per TMEM lane quarter, each owning half of the tile's columns
+constexpr int NTHREADS = (3 + EPI_WARPS) * 32;
 
 template <int BN> struct Cfg {
     static constexpr int BTILE = 2 * BN * 128;
-    static constexpr int PSTAGES = BN == 128 ? 2 : 3;                       // patch stages (2 planes each)
+    static constexpr int PSTAGES = BN == 32 ? 3 : 2;                        // patch stages (2 planes each)
     static constexpr int BSTAGES = BN == 128 ? 4 : (BN == 64 ? 5 : 6);
-    static constexpr int SMEM = 1024 + PSTAGES * 2 * PLANE_PITCH + BSTAGES * BTILE + 256;
+    // output staging tile of the TMA-store epilogue, [32-channel block][128 rows][128 B]: BN < 128 has room for a dedicated one
+    // (3x3 convolutions too); BN = 128 borrows the weight stages a 1x1 convolution does not need
+    static constexpr int STG_BYTES = BN < 128 ? BN * 512 : 0;
+    static constexpr int SMEM = 1024 + PSTAGES * 2 * PLANE_PITCH + BSTAGES * BTILE + STG_BYTES + 256;
     static constexpr int ACC_COLS = 2 * BN;
     static constexpr int NACC = 512 / ACC_COLS >= 4 ? 4 : 512 / ACC_COLS;
     static constexpr uint32_t TMEM_COLS = NACC * ACC_COLS;
 };
+
+template <int M> struct Mode { static constexpr int value = M; };      // compile-time store mode of the epilogue
 
 struct Params {
     const float* out_scale; const float* bias;
@@ -45,7 +51,9 @@ struct Params {
     float alpha, gain;
     int accumulate;          // y += result (the skip branch's data gradient lands on top of the main branch's)
     int bstages;             // weight stages in use (<= Cfg::BSTAGES)
-    int tma_store;           // 1x1 convolutions: the epilogue stages the tile in shared memory and stores it with TMA (below)
+    int tma_store;           // dense NHWC output: the epilogue stages the tile in shared memory and stores it with TMA (below)
+    int stg_off;             // staging tile, bytes after the first weight stage
+    int tx_shift, ty_shift;  // log2(tiles_x), log2(tiles_y) when both are powers of two, else -1
 };
 
 // Epilogue stores.  A thread owns one pixel (accumulator row); stored straight from registers, one 16-byte store instruction of a
@@ -62,7 +70,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_halo_pl_kernel(const __grid_
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t plane_base = base;                                          // [stage][plane]
     const uint32_t b_base = plane_base + C::PSTAGES * 2 * PLANE_PITCH;
-    const uint32_t bar_base = b_base + C::BSTAGES * C::BTILE;
+    const uint32_t bar_base = b_base + C::BSTAGES * C::BTILE + C::STG_BYTES;
     auto pl_full = [&](int s) { return bar_base + 8u * s; };                   // <= 4
     auto pl_empty = [&](int s) { return bar_base + 32u + 8u * s; };
     auto b_full = [&](int s) { return bar_base + 64u + 8u * s; };              // <= 6
@@ -76,16 +84,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_halo_pl_kernel(const __grid_
     const int PW = TW + 2 * pad, PH = TH + 2 * pad, PR = PW * PH;
     const int total_tiles = p.m_tiles * p.n_tiles;
     auto tile_coords = [&](int tile, int& x0, int& y0, int& b0, int& n0) {
-        const int nt = tile / p.m_tiles, mt = tile % p.m_tiles;
-        x0 = (mt % p.tiles_x) * TW;
-        y0 = ((mt / p.tiles_x) % p.tiles_y) * TH;
-        b0 = mt / (p.tiles_x * p.tiles_y);
+        int nt = 0, mt = tile;                             // n_tiles is 1..4: no division
+        while (mt >= p.m_tiles) { mt -= p.m_tiles; ++nt; }
+        if (p.tx_shift >= 0) {                             // power-of-two tile grid: shifts and masks
+            x0 = (mt & (p.tiles_x - 1)) * TW;
+            y0 = ((mt >> p.tx_shift) & (p.tiles_y - 1)) * TH;
+            b0 = mt >> (p.tx_shift + p.ty_shift);
+        } else {
+            x0 = (mt % p.tiles_x) * TW;
+            y0 = ((mt / p.tiles_x) % p.tiles_y) * TH;
+            b0 = mt / (p.tiles_x * p.tiles_y);
+        }
         n0 = nt * BN;
     };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::PSTAGES; ++s) { mbar_init(pl_full(s), 1); mbar_init(pl_empty(s), 1); }
-        for (int s = 0; s < C::NACC; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 4); }
+        for (int s = 0; s < C::NACC; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), EPI_WARPS); }
         for (int s = 0; s < C::BSTAGES; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
         fence_barrier_init();
     }
@@ -114,128 +129,150 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_halo_pl_kernel(const __grid_
                 }
             }
         }
-    } else if (warp == 6) {
+    } else if (warp == 2 + EPI_WARPS) {
         // ================= weight producer: one pre-packed tile per (tile, channel block, tap) =================
         if (elect_one()) {
-            int bt = 0;
+            int s = 0;
+            uint32_t sph = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int nt = tile / p.m_tiles;
+                int nt = 0;
+                for (int mt = tile; mt >= p.m_tiles; mt -= p.m_tiles) ++nt;
                 const unsigned char* wsrc = p.wp + (size_t)nt * p.nkb * taps * C::BTILE;
-                for (int i = 0; i < p.nkb * taps; ++i, ++bt) {
-                    const int s = bt % p.bstages;
-                    mbar_wait(b_empty(s), ((bt / p.bstages) & 1) ^ 1);
+                for (int i = 0; i < p.nkb * taps; ++i) {
+                    mbar_wait(b_empty(s), sph ^ 1);
                     mbar_expect_tx(b_full(s), C::BTILE);
                     bulk_load(b_base + s * C::BTILE, wsrc + (size_t)i * C::BTILE, C::BTILE, b_full(s));
+                    if (++s == p.bstages) { s = 0; sph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
+        // one thread; kept free of divisions and 64-bit descriptor arithmetic (see conv_halo.cu)
         if (elect_one()) {
             constexpr uint32_t idesc = idesc_bf16(BM, BN), idesc2 = idesc_bf16(BM, 2 * BN);
-            const uint32_t SBO = (uint32_t)PW * 128u;
-            int bt = 0, kbg = 0, sg = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++sg) {
-                const int abuf = sg % C::NACC;
-                mbar_wait(acc_empty(abuf), ((sg / C::NACC) & 1) ^ 1);
-                const uint32_t d = tmem_d + (uint32_t)(abuf * C::ACC_COLS);
-                for (int kb = 0; kb < p.nkb; ++kb, ++kbg) {
-                    const int ps = kbg % C::PSTAGES;
-                    mbar_wait(pl_full(ps), (kbg / C::PSTAGES) & 1);
-                    const uint32_t pl0 = plane_base + (uint32_t)(ps * 2) * PLANE_PITCH, pl1 = pl0 + PLANE_PITCH;
-                    for (int t = 0, dy = 0, dx = 0; t < taps; ++t, ++bt, dx = (dx + 1 == p.k ? 0 : dx + 1), dy += (dx == 0)) {
-                        const int s = bt % p.bstages;
-                        mbar_wait(b_full(s), (bt / p.bstages) & 1);
-                        tc_fence_after();
-                        const uint32_t arow = (uint32_t)(dy * PW + dx) * 128u;
-                        const uint32_t b0_ = b_base + s * C::BTILE;
-                        const int kqn = min(4, (p.ci - kb * 64) >> 4);      // 32-channel tail: the zero-filled half of the box is skipped
+            const uint32_t a_hi = (((uint32_t)PW * 128u) >> 4) | (1u << 14) | (2u << 29);       // A: K-major SWIZZLE_128B, 8-row groups PW rows apart
+            constexpr uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);                     // B: K-major SWIZZLE_128B, SBO 1024
+            constexpr uint32_t lo_f = 1u << 16;
+            const uint32_t nstages = (uint32_t)p.bstages, kdim = (uint32_t)p.k, row_wrap = (uint32_t)(PW - p.k) * 8u;
+            uint32_t s = 0, sph = 0, abuf = 0, aph = 0, ps = 0, pph = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(acc_empty(abuf), aph ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_d + abuf * (uint32_t)C::ACC_COLS;
+                int ci_left = p.ci;
+                for (int kb = 0; kb < p.nkb; ++kb, ci_left -= 64) {
+                    mbar_wait(pl_full(ps), pph);
+                    const uint32_t pl0 = (((plane_base + ps * 2u * PLANE_PITCH) & 0x3FFFFu) >> 4) | lo_f, pl1 = pl0 + (PLANE_PITCH >> 4);
+                    const int kqn = min(4, ci_left >> 4);               // 32-channel tail: the zero-filled half of the box is skipped
+                    uint32_t arow = 0, dx = 0;                          // (dy * PW + dx) * 128 B >> 4
+                    for (int t = 0; t < taps; ++t) {
+                        mbar_wait(b_full(s), sph);
+                        const uint32_t b0_ = (((b_base + s * C::BTILE) & 0x3FFFFu) >> 4) | lo_f;
 #pragma unroll
                         for (int kq = 0; kq < 4; ++kq) {
                             if (kq >= kqn) break;
-                            const uint64_t da0 = kmajor_desc_sbo(pl0 + arow + kq * 32, SBO), da1 = kmajor_desc_sbo(pl1 + arow + kq * 32, SBO);
-                            const uint64_t db = kmajor_desc(b0_ + kq * 32);
-                            mma_bf16(d, da0, db, idesc2, !(kb == 0 && t == 0 && kq == 0));     // [hi*hi | hi*lo] += A_hi * [B_hi ; B_lo]
-                            mma_bf16(d + BN, da1, db, idesc, 1);                               //          upper  += A_lo * B_hi
+                            const uint32_t db = b0_ + kq * 2;
+                            mma_f16_words(d, pl0 + arow + kq * 2, a_hi, db, b_hi, idesc2, !(kb == 0 && t == 0 && kq == 0));   // [hi*hi | hi*lo] += A_hi * [B_hi ; B_lo]
+                            mma_f16_words(d + BN, pl1 + arow + kq * 2, a_hi, db, b_hi, idesc, 1);                            //          upper  += A_lo * B_hi
                         }
                         mma_commit(b_empty(s));
+                        if (++s == nstages) { s = 0; sph ^= 1; }
+                        arow += 8;
+                        if (++dx == kdim) { dx = 0; arow += row_wrap; }
                     }
                     mma_commit(pl_empty(ps));
+                    if (++ps == C::PSTAGES) { ps = 0; pph ^= 1; }
                 }
                 mma_commit(acc_full(abuf));
+                if (++abuf == C::NACC) { abuf = 0; aph ^= 1; }
             }
         }
-    } else if (warp >= 2 && warp < 6) {
+    } else if (warp >= 2 && warp < 2 + EPI_WARPS) {
         // ================= epilogue warps =================
-        const int q4 = warp & 3;
+        const int ew = warp - 2, q4 = warp & 3;
         const int er = q4 * 32 + lane;                    // accumulator row = pixel (y*8 + x)
-        const uint32_t stg = b_base + (uint32_t)p.bstages * C::BTILE;         // staging tile: [32-channel block][128 rows][128 B]
-        const uint32_t stg_row = stg + (uint32_t)er * 128u;
-        int sg = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++sg) {
+        constexpr int COLS = BN / 2;                      // columns this thread owns
+        const int cstart = (ew >> 2) * COLS;
+        constexpr int EPI_THREADS = EPI_WARPS * 32;
+        const uint32_t stg = b_base + (uint32_t)p.stg_off;                    // staging tile: [32-channel block][128 rows][128 B]
+        const uint32_t stg_thr = stg + (uint32_t)er * 128u + (uint32_t)(cstart >> 5) * (128u * 128u);
+        const uint32_t stg_x = (uint32_t)(((cstart & 31) >> 2) ^ (er & 7));
+        const float alpha_eff = p.act == 3 ? p.alpha : 1.f, gain = p.gain;
+        const int smode = p.tma_store ? 0 : (p.ys[1] == 1 ? 1 : 2);
+        const uint32_t lane_addr = tmem_d + ((uint32_t)(q4 * 32) << 16) + (uint32_t)cstart;
+        uint32_t abuf = 0, aph = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             int x0, y0, b0, n0;
             tile_coords(tile, x0, y0, b0, n0);
             const int ex = x0 + (er & 7), ey = y0 + (er >> 3);
             const bool inside = ex < p.w && ey < p.h;
             float* yrow = p.y + (long long)b0 * p.ys[0] + (long long)ey * p.ys[2] + (long long)ex * p.ys[3];
-            const float* osc = p.out_scale ? p.out_scale + (long long)b0 * p.co + n0 : nullptr;
-            const float* bsp = p.bias ? p.bias + n0 : nullptr;
-            const uint32_t lane_addr = tmem_d + ((uint32_t)(q4 * 32) << 16);
-            const int abuf = sg % C::NACC;
-            mbar_wait(acc_full(abuf), (sg / C::NACC) & 1);
+            float* ydense = yrow + n0 + cstart;
+            const float* osc = p.out_scale ? p.out_scale + (long long)b0 * p.co + n0 + cstart : nullptr;
+            const float* bsp = p.bias ? p.bias + n0 + cstart : nullptr;
+            mbar_wait(acc_full(abuf), aph);
             tc_fence_after();
-            if (p.tma_store) {
-                // the previous tile's TMA stores must have READ the staging tile before it is overwritten
-                if (warp == 2 && lane == 0) bulk_wait_read_all();
-                named_bar_sync(1, 128);
-            }
-#pragma unroll 1
-            for (int c = 0; c < BN / 16; ++c) {
+            // the whole column range in one round of TMEM loads; the accumulator goes back to the MMA warp before the stores
+            float racc[COLS];
+#pragma unroll
+            for (int c = 0; c < COLS / 16; ++c) {
                 uint32_t v[16], v2[16];
-                const uint32_t col = (uint32_t)(abuf * C::ACC_COLS + c * 16);
+                const uint32_t col = abuf * (uint32_t)C::ACC_COLS + (uint32_t)(c * 16);
                 tmem_ld16_async(lane_addr + col, v);
                 tmem_ld16_async(lane_addr + col + BN, v2);
                 tmem_ld_wait();
                 reg_fence(v); reg_fence(v2);
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    float o[4] = {__uint_as_float(v[j]) + __uint_as_float(v2[j]), __uint_as_float(v[j + 1]) + __uint_as_float(v2[j + 1]),
-                                  __uint_as_float(v[j + 2]) + __uint_as_float(v2[j + 2]), __uint_as_float(v[j + 3]) + __uint_as_float(v2[j + 3])};
-                    const int cbase = c * 16 + j;
-                    if (osc) { const float4 t = ldg4(osc + cbase); o[0] *= t.x; o[1] *= t.y; o[2] *= t.z; o[3] *= t.w; }
-                    if (bsp) { const float4 t = ldg4(bsp + cbase); o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w; }
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float val = o[e];
-                        if (p.act == 3) val = val > 0.f ? val : val * p.alpha;
-                        o[e] = val * p.gain;
-                    }
-                    if (p.tma_store) {
-                        const int blk = cbase >> 5, chunk = (cbase & 31) >> 2;
-                        sts4(stg_row + (uint32_t)blk * (128u * 128u) + (uint32_t)((chunk ^ (er & 7)) << 4),
-                             __float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3]));
-                    } else if (inside) {
-                        const int cb = n0 + cbase;
-                        if (p.ys[1] == 1) {
-                            if (p.accumulate) { const float4 t = *reinterpret_cast<const float4*>(yrow + cb); o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w; }
-                            st4(yrow + cb, make_float4(o[0], o[1], o[2], o[3]));
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                float* dst = yrow + (long long)(cb + e) * p.ys[1];
-                                *dst = p.accumulate ? *dst + o[e] : o[e];
-                            }
-                        }
-                    }
-                }
+                for (int j = 0; j < 16; ++j) racc[c * 16 + j] = __uint_as_float(v[j]) + __uint_as_float(v2[j]);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty(abuf));
-            if (p.tma_store) {
+            if (++abuf == C::NACC) { abuf = 0; aph ^= 1; }
+            if (smode == 0) {
+                // the previous tile's TMA stores must have READ the staging tile before it is overwritten
+                if (ew == 0 && lane == 0) bulk_wait_read_all();
+                named_bar_sync(1, EPI_THREADS);
+            }
+            // out_scale, bias, activation, gain on 4 channels, then the store.  MODE: 0 = swizzled staging tile for the TMA store
+            // (or reduce-add), 1 = dense NHWC 16-byte stores, 2 = any strides.
+            auto finish_all = [&](auto mode) {
+                constexpr int MODE = decltype(mode)::value;
+#pragma unroll
+                for (int cbase = 0; cbase < COLS; cbase += 4) {
+                    const float4 sc = osc ? ldg4(osc + cbase) : make_float4(1.f, 1.f, 1.f, 1.f);
+                    const float4 bi = bsp ? ldg4(bsp + cbase) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, biv[4] = {bi.x, bi.y, bi.z, bi.w};
+                    float o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float val = fmaf(racc[cbase + e], scv[e], biv[e]);
+                        o[e] = (val > 0.f ? val : val * alpha_eff) * gain;
+                    }
+                    if (MODE == 0) {
+                        sts4(stg_thr + (uint32_t)(cbase >> 5) * (128u * 128u) + ((stg_x ^ (uint32_t)((cbase & 31) >> 2)) << 4),
+                             __float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3]));
+                    } else if (MODE == 1) {
+                        if (inside) {
+                            if (p.accumulate) { const float4 t = *reinterpret_cast<const float4*>(ydense + cbase); o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w; }
+                            st4(ydense + cbase, make_float4(o[0], o[1], o[2], o[3]));
+                        }
+                    } else if (inside) {
+                        const int cb = n0 + cstart + cbase;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float* dst = yrow + (long long)(cb + e) * p.ys[1];
+                            *dst = p.accumulate ? *dst + o[e] : o[e];
+                        }
+                    }
+                }
+            };
+            if (smode == 0) finish_all(Mode<0>{}); else if (smode == 1) finish_all(Mode<1>{}); else finish_all(Mode<2>{});
+            if (smode == 0) {
                 fence_proxy_async();                      // the staging writes become visible to the async proxy (TMA)
-                named_bar_sync(1, 128);
-                if (warp == 2 && lane == 0) {
+                named_bar_sync(1, EPI_THREADS);
+                if (ew == 0 && lane == 0) {
                     for (int blk = 0; blk < BN / 32; ++blk) {
                         if (p.accumulate) tma_reduce_add_4d(&ymap, stg + (uint32_t)blk * (128u * 128u), n0 + 32 * blk, x0, y0, b0);
                         else tma_store_4d(&ymap, stg + (uint32_t)blk * (128u * 128u), n0 + 32 * blk, x0, y0, b0);
@@ -244,7 +281,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_halo_pl_kernel(const __grid_
                 }
             }
         }
-        if (p.tma_store && warp == 2 && lane == 0) bulk_wait_all();
+        if (p.tma_store && ew == 0 && lane == 0) bulk_wait_all();
     }
     tc_fence_before();
     __syncthreads();
@@ -267,9 +304,10 @@ static int launch(const CUtensorMap& map, const CUtensorMap& ymap, Params& tp, d
         configured = true;
     }
     tp.bstages = C::BSTAGES;
-    if (tp.tma_store) {
-        // a 1x1 convolution streams one weight tile per channel block: two stages are plenty, the rest of the region is the staging tile
-        if ((C::BSTAGES - 2) * C::BTILE >= BN * 512) tp.bstages = 2; else tp.tma_store = 0;
+    tp.stg_off = C::BSTAGES * C::BTILE;
+    if (tp.tma_store && !C::STG_BYTES) {
+        // BN = 128: only a 1x1 convolution (one weight tile per channel block: two stages are plenty) has room for the staging tile
+        if (tp.k == 1 && (C::BSTAGES - 2) * C::BTILE >= BN * 512) { tp.bstages = 2; tp.stg_off = 2 * C::BTILE; } else tp.tma_store = 0;
     }
     conv_halo_pl_kernel<BN><<<grid, NTHREADS, C::SMEM, st>>>(map, ymap, tp);
     return launched("conv_halo_pl");
@@ -303,10 +341,13 @@ int conv_fwd_halo_pl(const void* x_planes, const ConvParams& p, int accumulate, 
     tp.n_tiles = p.co / bn;
     tp.nkb = (p.ci + 63) / 64;
     tp.act = p.act; tp.alpha = p.alpha; tp.gain = p.gain; tp.accumulate = accumulate;
-    // TMA-store epilogue: 1x1 convolutions into a dense NHWC tensor
+    auto log2_exact = [](int v) { int l = 0; while ((1 << l) < v) ++l; return (1 << l) == v ? l : -1; };
+    tp.tx_shift = log2_exact(tp.tiles_x); tp.ty_shift = log2_exact(tp.tiles_y);
+    if (tp.tx_shift < 0 || tp.ty_shift < 0) tp.tx_shift = tp.ty_shift = -1;
+    // TMA-store epilogue: dense NHWC output tensors
     CUtensorMap ymap = map;
     tp.tma_store = 0;
-    if (p.k == 1 && p.ys[1] == 1 && p.ys[3] == p.co && p.ys[2] == (long long)p.w * p.co && p.ys[0] == (long long)p.h * p.w * p.co &&
+    if (p.ys[1] == 1 && p.ys[3] == p.co && p.ys[2] == (long long)p.w * p.co && p.ys[0] == (long long)p.h * p.w * p.co &&
         ((uintptr_t)p.y & 15) == 0) {
         rc = tc::make_nhwc_map(&ymap, p.y, p.n, p.h, p.w, p.co, halopl::TW, halopl::TH, 1, "conv_fwd_halo_pl(y)");
         if (rc) return rc;
