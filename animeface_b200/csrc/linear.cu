@@ -20,23 +20,66 @@ namespace sg2 {
 namespace lin {
 
 
-// CTA = 16 output features (8 warps x 2) x all batch rows; the x tile [32 rows][256 k] is staged in shared memory so x is read
-// once per CTA (not once per feature) and every weight row once per 32 batch rows; lanes stride k with 128-bit loads
-constexpr int FWD_NT = 16, FWD_RB = 32, FWD_KC = 256;
+// CTA = FPW * 8 output features (8 warps, FPW features each) x a slice of FWD_KS input features x all batch rows (32 at a time).
+// A warp keeps its weight-row slices in registers (loaded first, so their latency hides behind the staging of x); x is staged
+// in shared memory as [32 rows][256 k] tiles; the 32 row sums of a feature are reduced across the lanes by a halving butterfly
+// (31 shuffles instead of 32 full reductions).  K larger than one slice is split over blockIdx.y: the CTAs write partial sums
+// and linear_fwd_finish_kernel adds them in slice order (fixed order -> run-to-run identical) and applies the epilogue.
+constexpr int FWD_RB = 32, FWD_KC = 256, FWD_KS = 512;
 
+// v[r] (r = 0..31) holds this lane's partial of row r; returns the full sum of row `lane`
+__device__ __forceinline__ float row_sums_to_lanes(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            // keep the half of the values whose row index has bit `off` equal to this lane's; hand the other half over
+            const float keep = upper ? v[i + off] : v[i], send = upper ? v[i] : v[i + off];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+template <int FPW>
 __global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                                                         float* __restrict__ y, int B, int K, int N, float coef, float gain, float slope) {
+                                                         float* __restrict__ y, float* __restrict__ partial, int B, int K, int N, float coef,
+                                                         float gain, float slope) {
     __shared__ __align__(16) float xs[FWD_RB][FWD_KC];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n0 = blockIdx.x * FWD_NT + warp * 2;
+    const int n0 = (blockIdx.x * 8 + warp) * FPW;
+    const int ks0 = blockIdx.y * FWD_KS, ks1 = min(K, ks0 + FWD_KS);
     const bool vec = (K & 3) == 0 && (((uintptr_t)x | (uintptr_t)w) & 15) == 0;
+    // this warp's weight slices: [feature][256-tile][128-column half] float4 per lane
+    float4 wv[FPW][FWD_KS / FWD_KC][2];
+#pragma unroll
+    for (int f = 0; f < FPW; ++f)
+#pragma unroll
+        for (int t = 0; t < FWD_KS / FWD_KC; ++t)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int n = n0 + f, k = ks0 + t * FWD_KC + h * 128 + lane * 4;
+                float4 v = f4zero();
+                if (n < N && k < ks1) {
+                    const float* wr = w + (long long)n * K + k;
+                    if (vec) v = ldg4(wr);
+                    else { v.x = __ldg(wr); v.y = k + 1 < ks1 ? __ldg(wr + 1) : 0.f; v.z = k + 2 < ks1 ? __ldg(wr + 2) : 0.f; v.w = k + 3 < ks1 ? __ldg(wr + 3) : 0.f; }
+                }
+                wv[f][t][h] = v;
+            }
     for (int b0 = 0; b0 < B; b0 += FWD_RB) {
         const int rows = min(FWD_RB, B - b0);
-        float acc[2][FWD_RB];
+        float acc[FPW][FWD_RB];
 #pragma unroll
-        for (int r = 0; r < FWD_RB; ++r) acc[0][r] = acc[1][r] = 0.f;
-        for (int k0 = 0; k0 < K; k0 += FWD_KC) {
-            const int kc = min(FWD_KC, K - k0);
+        for (int f = 0; f < FPW; ++f)
+#pragma unroll
+            for (int r = 0; r < FWD_RB; ++r) acc[f][r] = 0.f;
+#pragma unroll
+        for (int t = 0; t < FWD_KS / FWD_KC; ++t) {
+            const int k0 = ks0 + t * FWD_KC;
+            if (k0 >= ks1) break;
+            const int kc = min(FWD_KC, ks1 - k0);
             __syncthreads();
             if (vec) {
                 for (int i = threadIdx.x; i < FWD_RB * (FWD_KC / 4); i += 256) {
@@ -53,41 +96,40 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict
             }
             __syncthreads();
 #pragma unroll
-            for (int f = 0; f < 2; ++f) {
-                const int n = n0 + f;
-                if (n >= N) continue;
-                const float* wr = w + (long long)n * K + k0;
-                for (int c = lane * 4; c < kc; c += 128) {
-                    float4 wv;
-                    if (vec) wv = ldg4(wr + c);
-                    else {
-                        wv.x = __ldg(wr + c); wv.y = c + 1 < kc ? __ldg(wr + c + 1) : 0.f;
-                        wv.z = c + 2 < kc ? __ldg(wr + c + 2) : 0.f; wv.w = c + 3 < kc ? __ldg(wr + c + 3) : 0.f;
-                    }
+            for (int h = 0; h < 2; ++h)
 #pragma unroll
-                    for (int r = 0; r < FWD_RB; ++r) {
-                        const float4 xv = *reinterpret_cast<const float4*>(&xs[r][c]);
-                        acc[f][r] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, fmaf(xv.z, wv.z, fmaf(xv.w, wv.w, acc[f][r]))));
+                for (int r = 0; r < FWD_RB; ++r) {
+                    const float4 xv = *reinterpret_cast<const float4*>(&xs[r][h * 128 + lane * 4]);
+#pragma unroll
+                    for (int f = 0; f < FPW; ++f) {
+                        const float4 q = wv[f][t][h];
+                        acc[f][r] = fmaf(xv.x, q.x, fmaf(xv.y, q.y, fmaf(xv.z, q.z, fmaf(xv.w, q.w, acc[f][r]))));
                     }
+                }
+        }
+#pragma unroll
+        for (int f = 0; f < FPW; ++f) {
+            const int n = n0 + f;
+            const float mine = row_sums_to_lanes(acc[f], lane);
+            if (n < N && lane < rows) {
+                if (partial) partial[((long long)blockIdx.y * B + b0 + lane) * N + n] = mine;
+                else {
+                    float t = (coef * mine + (bias ? __ldg(bias + n) : 0.f)) * gain;
+                    y[(long long)(b0 + lane) * N + n] = t > 0.f ? t : t * slope;
                 }
             }
         }
-#pragma unroll
-        for (int f = 0; f < 2; ++f) {
-            const int n = n0 + f;
-            float mine = 0.f;
-#pragma unroll
-            for (int r = 0; r < FWD_RB; ++r) {
-                const float sum = warp_sum(acc[f][r]);
-                if (lane == r) mine = sum;
-            }
-            if (n < N && lane < rows) {
-                float t = (coef * mine + (bias ? __ldg(bias + n) : 0.f)) * gain;
-                t = t > 0.f ? t : t * slope;
-                y[(long long)(b0 + lane) * N + n] = t;
-            }
-        }
     }
+}
+
+__global__ void __launch_bounds__(256) linear_fwd_finish_kernel(const float* __restrict__ partial, const float* __restrict__ bias, float* __restrict__ y,
+                                                                int B, int N, int splits, float coef, float gain, float slope) {
+    const long long i = blockIdx.x * 256LL + threadIdx.x;
+    if (i >= (long long)B * N) return;
+    float s = 0.f;
+    for (int sp = 0; sp < splits; ++sp) s += partial[(long long)sp * B * N + i];
+    const float t = (coef * s + (bias ? __ldg(bias + (int)(i % N)) : 0.f)) * gain;
+    y[i] = t > 0.f ? t : t * slope;
 }
 
 __device__ __forceinline__ float gu_of(const float* gy, const float* y, long long i, float gain, float slope) {
@@ -120,7 +162,8 @@ __global__ void __launch_bounds__(128) linear_bwd_data_kernel(const float* __res
             gu[r][c] = r < rows ? gu_of(gy, y, (long long)(b0 + r) * N + n0 + c, gain, slope) : 0.f;
         }
         __syncthreads();
-        for (int c = warp; c < nn; c += 4) {
+#pragma unroll 8
+        for (int c = warp; c < nn; c += 4) {           // unrolled: 8 weight rows in flight
             const float* wr = w + (long long)(n0 + c) * K;
             float wv[KV];
             if (vec) {
@@ -161,7 +204,8 @@ __global__ void __launch_bounds__(128) linear_bwd_weight_kernel(const float* __r
     const bool vec = (K & 3) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)gw & 15) == 0;
     float4 acc = f4zero();
     float sb = 0.f;
-    for (int b = 0; b < B; ++b) {
+#pragma unroll 8
+    for (int b = 0; b < B; ++b) {                     // unrolled: 8 rows of loads in flight (the loop is pure load latency otherwise)
         const float g = gu_of(gy, y, (long long)b * N + n, gain, slope);
         sb += g;
         const float* xr = x + (long long)b * K;
@@ -202,12 +246,32 @@ __global__ void __launch_bounds__(128) pixelnorm_kernel(const float* __restrict_
 
 using namespace sg2;
 
+// bytes of the partial-sum buffer sg2_linear_fwd needs (0: K fits one slice, no second pass)
+extern "C" long long sg2_linear_fwd_workspace(int B, int K, int N) {
+    const long long splits = ceil_div(K, lin::FWD_KS);
+    return splits > 1 ? splits * B * N * (long long)sizeof(float) : 0;
+}
+
 extern "C" int sg2_linear_fwd(const float* x, const float* w, const float* bias, float* y, int B, int K, int N,
-                              float coef, float gain, float slope, sg2_stream_t stream) {
+                              float coef, float gain, float slope, void* workspace, sg2_stream_t stream) {
     SG2_REQUIRE(x && w && y, "linear_fwd: null pointer");
     SG2_REQUIRE(B > 0 && K > 0 && N > 0, "linear_fwd: empty tensor");
-    lin::linear_fwd_kernel<<<(unsigned)ceil_div(N, lin::FWD_NT), 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, B, K, N, coef, gain, slope);
-    return launched("linear_fwd");
+    const int splits = (int)ceil_div(K, lin::FWD_KS);
+    SG2_REQUIRE(splits == 1 || workspace, "linear_fwd: K spans several slices and needs the workspace of sg2_linear_fwd_workspace");
+    float* partial = splits > 1 ? (float*)workspace : nullptr;
+    cudaStream_t st = (cudaStream_t)stream;
+    // two features per warp when that still gives every SM a CTA (the wide discriminator layer), else one
+    if (ceil_div(N, 16) * splits >= num_sms()) {
+        dim3 grid((unsigned)ceil_div(N, 16), (unsigned)splits);
+        lin::linear_fwd_kernel<2><<<grid, 256, 0, st>>>(x, w, bias, y, partial, B, K, N, coef, gain, slope);
+    } else {
+        dim3 grid((unsigned)ceil_div(N, 8), (unsigned)splits);
+        lin::linear_fwd_kernel<1><<<grid, 256, 0, st>>>(x, w, bias, y, partial, B, K, N, coef, gain, slope);
+    }
+    int rc = launched("linear_fwd");
+    if (rc || splits == 1) return rc;
+    lin::linear_fwd_finish_kernel<<<(unsigned)ceil_div((long long)B * N, 256), 256, 0, st>>>(partial, bias, y, B, N, splits, coef, gain, slope);
+    return launched("linear_fwd_finish");
 }
 
 extern "C" int sg2_linear_bwd_data(const float* gy, const float* y, const float* w, float* gx, int B, int K, int N,

@@ -22,86 +22,133 @@ __device__ __forceinline__ void split4(const float4& v, uint2& hi, uint2& lo) {
     lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
 }
 
+// Thread layout of both kernels: a block covers a chunk of CW channels (64, or 32 for 32-channel tensors so that no thread
+// idles) x a slice of the pixels; TPP = CW / 4 threads share a pixel (one float4 each), 256 / TPP pixels per pass.
+__device__ __forceinline__ int chunk_width(int c) { return (c % 64 == 0 || c > 32) ? 64 : (c > 16 ? 32 : 16); }
+
 __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                                            __nv_bfloat16* __restrict__ planes, long long plane_stride, int hw, int c, int slice) {
-    const int q = threadIdx.x & 15, pl = threadIdx.x >> 4;
-    const int c0 = blockIdx.x * 64 + q * 4, b = blockIdx.y;
+    const int cw = chunk_width(c), tpp = cw >> 2, rows = 256 / tpp;
+    const int q = threadIdx.x % tpp, pl = threadIdx.x / tpp;
+    const int c0 = blockIdx.x * cw + q * 4, b = blockIdx.y;
     const int beg = blockIdx.z * slice, end = min(hw, beg + slice);
     if (c0 >= c) return;
     const long long base = (long long)b * hw * c + c0;
     const float4 sc = scale ? ldg4(scale + (long long)b * c + c0) : make_float4(1.f, 1.f, 1.f, 1.f);
-    for (int i = beg + pl; i < end; i += 16) {
-        const long long o = base + (long long)i * c;
+    auto emit = [&](long long o, const float4& v) {
         uint2 hi, lo;
-        split4(mul4(ldg4(x + o), sc), hi, lo);
+        split4(mul4(v, sc), hi, lo);
         *reinterpret_cast<uint2*>(planes + o) = hi;
         *reinterpret_cast<uint2*>(planes + plane_stride + o) = lo;
+    };
+    // four pixels per iteration: their loads are in flight together before the first store
+    int i = beg + pl;
+    const long long step = (long long)rows * c;
+    for (; i + 3 * rows < end; i += 4 * rows) {
+        const long long o = base + (long long)i * c;
+        const float4 v0 = ldg4(x + o), v1 = ldg4(x + o + step), v2 = ldg4(x + o + 2 * step), v3 = ldg4(x + o + 3 * step);
+        emit(o, v0); emit(o + step, v1); emit(o + 2 * step, v2); emit(o + 3 * step, v3);
+    }
+    for (; i < end; i += rows) {
+        const long long o = base + (long long)i * c;
+        emit(o, ldg4(x + o));
     }
 }
 
 // per-block partial sums -> part[(slice, b, c)] (no atomics: the caller's second pass adds the slices in a fixed order)
-__device__ __forceinline__ void block_reduce_part(float4 acc, float (*sh)[68], float* out_row, int c, int cbase) {
-    const int q = threadIdx.x & 15, pl = threadIdx.x >> 4;
-    sh[pl][q * 4 + 0] = acc.x; sh[pl][q * 4 + 1] = acc.y; sh[pl][q * 4 + 2] = acc.z; sh[pl][q * 4 + 3] = acc.w;
+__device__ __forceinline__ void block_reduce_part(float4 acc, float* sh, float* out_row, int c, int cbase, int cw) {
+    const int tpp = cw >> 2, rows = 256 / tpp, pitch = cw + 4;
+    const int q = threadIdx.x % tpp, pl = threadIdx.x / tpp;
+    float* mine = sh + pl * pitch + q * 4;
+    mine[0] = acc.x; mine[1] = acc.y; mine[2] = acc.z; mine[3] = acc.w;
     __syncthreads();
-    if (threadIdx.x < 64) {
+    if ((int)threadIdx.x < cw) {
         float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) s += sh[i][threadIdx.x];
+        for (int i = 0; i < rows; ++i) s += sh[i * pitch + threadIdx.x];
         const int cc = cbase + threadIdx.x;
         if (cc < c) out_row[cc] = s;
     }
     __syncthreads();
 }
 
+// gu = g * lrelu'(y) and u = the pre-activation value, for 4 channels
+__device__ __forceinline__ void lrelu_grad4(const float4& g, const float4& yv, float alpha, float inv_alpha, float4& gu, float4& u) {
+    gu.x = yv.x > 0.f ? g.x : g.x * alpha; u.x = yv.x > 0.f ? yv.x : yv.x * inv_alpha;
+    gu.y = yv.y > 0.f ? g.y : g.y * alpha; u.y = yv.y > 0.f ? yv.y : yv.y * inv_alpha;
+    gu.z = yv.z > 0.f ? g.z : g.z * alpha; u.z = yv.z > 0.f ? yv.z : yv.z * inv_alpha;
+    gu.w = yv.w > 0.f ? g.w : g.w * alpha; u.w = yv.w > 0.f ? yv.w : yv.w * inv_alpha;
+}
+
+// POOLED: gy is the gradient of a 2x2 average pooling's OUTPUT ([n, hw/4, c], full-resolution width pool_w).  The pooling
+// adjoint (broadcast over the 2x2 window, times gscale) is applied while reading, so the full-size gradient is never written
+// or read: a thread walks POOLED pixels -- one load of g, the four y loads of its window in flight together, four stores.
+// `slice` then counts pooled pixels.
+template <bool POOLED>
 __global__ void __launch_bounds__(256) bwd_prep_planes_kernel(const float* __restrict__ gy, const float* __restrict__ y,
                                                               const float* __restrict__ noise, const float* __restrict__ bias,
                                                               const float* __restrict__ d, __nv_bfloat16* __restrict__ planes,
                                                               long long plane_stride, float* __restrict__ part_gb, float* __restrict__ part_gd,
                                                               int n, int hw, int c, int slice, float alpha, int pool_w, float gscale) {
-    __shared__ float sh[16][68];
-    const int q = threadIdx.x & 15, pl = threadIdx.x >> 4;
-    const int c0 = blockIdx.x * 64 + q * 4, b = blockIdx.y;
-    const int beg = blockIdx.z * slice, end = min(hw, beg + slice);
+    __shared__ float sh[64 * 36];                          // rows x (CW + 4): 16 x 68 or 32 x 36
+    const int cw = chunk_width(c), tpp = cw >> 2, rows = 256 / tpp;
+    const int q = threadIdx.x % tpp, pl = threadIdx.x / tpp;
+    const int c0 = blockIdx.x * cw + q * 4, b = blockIdx.y;
+    const int items = POOLED ? hw >> 2 : hw;
+    const int beg = blockIdx.z * slice, end = min(items, beg + slice);
     float4 sgu = f4zero(), sgd = f4zero();
     if (c0 < c) {
         const long long base = (long long)b * hw * c + c0;
         const float4 dv = d ? ldg4(d + (long long)b * c + c0) : make_float4(1.f, 1.f, 1.f, 1.f);
         const float4 bv = bias ? ldg4(bias + c0) : f4zero();
         const float inv_alpha = 1.f / alpha;
-        // pool_w > 0: gy is the gradient of a 2x2 average pooling's OUTPUT ([n, hw/4, c], full-resolution width pool_w): the
-        // pooling adjoint (broadcast over the 2x2 window, times gscale) is applied while reading, so the full-size gradient is
-        // never written or read
-        const long long gbase = pool_w > 0 ? (long long)b * (hw >> 2) * c + c0 : base;
-        for (int i = beg + pl; i < end; i += 16) {
-            const long long o = base + (long long)i * c;
-            long long go = o;
-            if (pool_w > 0) { const int py = i / pool_w, px = i - py * pool_w; go = gbase + ((long long)(py >> 1) * (pool_w >> 1) + (px >> 1)) * c; }
-            const float4 g = scale4(ldg4(gy + go), gscale);
+        auto emit = [&](long long o, int pix, const float4& g, const float4& yv) {
             float4 gu = g, u = f4zero();
-            if (y) {
-                const float4 yv = ldg4(y + o);
-                gu.x = yv.x > 0.f ? g.x : g.x * alpha; u.x = yv.x > 0.f ? yv.x : yv.x * inv_alpha;
-                gu.y = yv.y > 0.f ? g.y : g.y * alpha; u.y = yv.y > 0.f ? yv.y : yv.y * inv_alpha;
-                gu.z = yv.z > 0.f ? g.z : g.z * alpha; u.z = yv.z > 0.f ? yv.z : yv.z * inv_alpha;
-                gu.w = yv.w > 0.f ? g.w : g.w * alpha; u.w = yv.w > 0.f ? yv.w : yv.w * inv_alpha;
-            }
+            if (y) lrelu_grad4(g, yv, alpha, inv_alpha, gu, u);
             uint2 hi, lo;
             split4(mul4(gu, dv), hi, lo);
             *reinterpret_cast<uint2*>(planes + o) = hi;
             *reinterpret_cast<uint2*>(planes + plane_stride + o) = lo;
             sgu = add4(sgu, gu);
             if (part_gd) {
-                const float nz = noise ? __ldg(noise + (long long)b * hw + i) : 0.f;
+                const float nz = noise ? __ldg(noise + (long long)b * hw + pix) : 0.f;
                 sgd.x = fmaf(gu.x, u.x - bv.x - nz, sgd.x); sgd.y = fmaf(gu.y, u.y - bv.y - nz, sgd.y);
                 sgd.z = fmaf(gu.z, u.z - bv.z - nz, sgd.z); sgd.w = fmaf(gu.w, u.w - bv.w - nz, sgd.w);
+            }
+        };
+        if (POOLED) {
+            const int pw2 = pool_w >> 1;
+            const long long gbase = (long long)b * (hw >> 2) * c + c0;
+            for (int i = beg + pl; i < end; i += rows) {
+                const int py = i / pw2, px = i - py * pw2;
+                const float4 g = scale4(ldg4(gy + gbase + (long long)i * c), gscale);
+                const int p00 = (2 * py) * pool_w + 2 * px;
+                const int pix[4] = {p00, p00 + 1, p00 + pool_w, p00 + pool_w + 1};
+                float4 yv[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) yv[e] = y ? ldg4(y + base + (long long)pix[e] * c) : f4zero();
+#pragma unroll
+                for (int e = 0; e < 4; ++e) emit(base + (long long)pix[e] * c, pix[e], g, yv[e]);
+            }
+        } else {
+            // two pixels per iteration: both pairs of loads in flight before the first store
+            int i = beg + pl;
+            for (; i + rows < end; i += 2 * rows) {
+                const long long o0 = base + (long long)i * c, o1 = o0 + (long long)rows * c;
+                const float4 g0 = scale4(ldg4(gy + o0), gscale), g1 = scale4(ldg4(gy + o1), gscale);
+                const float4 y0 = y ? ldg4(y + o0) : f4zero(), y1 = y ? ldg4(y + o1) : f4zero();
+                emit(o0, i, g0, y0);
+                emit(o1, i + rows, g1, y1);
+            }
+            if (i < end) {
+                const long long o = base + (long long)i * c;
+                emit(o, i, scale4(ldg4(gy + o), gscale), y ? ldg4(y + o) : f4zero());
             }
         }
         if (part_gd) { sgd.x /= dv.x; sgd.y /= dv.y; sgd.z /= dv.z; sgd.w /= dv.w; }
     }
     const long long row = ((long long)blockIdx.z * n + b) * c;
-    block_reduce_part(sgu, sh, part_gb + row, c, blockIdx.x * 64);
-    if (part_gd) block_reduce_part(sgd, sh, part_gd + row, c, blockIdx.x * 64);
+    block_reduce_part(sgu, sh, part_gb + row, c, blockIdx.x * cw, cw);
+    if (part_gd) block_reduce_part(sgd, sh, part_gd + row, c, blockIdx.x * cw, cw);
 }
 
 // out[i] = sum_s part[s][i] in slice order (deterministic); i over n*c
@@ -113,12 +160,19 @@ __global__ void __launch_bounds__(256) sum_slices_kernel(const float* __restrict
     out[i] = s;
 }
 
-static void pick_grid_pl(int n, int hw, int c, dim3& grid, int& slice) {
-    const int cchunks = (c + 63) / 64;
+static int host_chunk_width(int c) { return (c % 64 == 0 || c > 32) ? 64 : (c > 16 ? 32 : 16); }
+
+// `items` = pixels a thread walks (pooled pixels for the pooled prologue); the slice count is the same for both so that one
+// workspace size serves either form
+static void pick_grid_pl(int n, int hw, int c, dim3& grid, int& slice, bool pooled = false) {
+    const int cw = host_chunk_width(c);
+    const int cchunks = (c + cw - 1) / cw;
     long long want = std::max<long long>(1, (4LL * num_sms()) / ((long long)cchunks * n));
     int slices = (int)std::min<long long>(std::min<long long>(want, 64), ceil_div(hw, 64));
-    slice = (int)ceil_div(hw, slices);
-    slices = (int)ceil_div(hw, slice);
+    const int items = pooled ? hw / 4 : hw;
+    slices = std::max(1, std::min(slices, items));
+    slice = (int)ceil_div(items, slices);
+    slices = (int)ceil_div(items, slice);
     grid = dim3(cchunks, n, slices);
 }
 
@@ -153,12 +207,16 @@ extern "C" int sg2_bwd_prep_planes(const float* gy, const float* y, const float*
                 "bwd_prep_planes: pooled gradient needs an even full-resolution width and height (w=%d, hw=%d)", pool_w, hw);
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid; int slice;
-    pick_grid_pl(n, hw, c, grid, slice);
+    pick_grid_pl(n, hw, c, grid, slice, pool_w > 0);
     const long long nc = (long long)n * c;
     float* part_gb = (float*)workspace;
     float* part_gd = gd ? part_gb + (long long)grid.z * nc : nullptr;
-    bwd_prep_planes_kernel<<<grid, 256, 0, st>>>(gy, y, noise, bias, d, (__nv_bfloat16*)planes, (long long)n * hw * c, part_gb, part_gd,
-                                                 n, hw, c, slice, alpha, pool_w, gscale);
+    if (pool_w > 0)
+        bwd_prep_planes_kernel<true><<<grid, 256, 0, st>>>(gy, y, noise, bias, d, (__nv_bfloat16*)planes, (long long)n * hw * c, part_gb, part_gd,
+                                                           n, hw, c, slice, alpha, pool_w, gscale);
+    else
+        bwd_prep_planes_kernel<false><<<grid, 256, 0, st>>>(gy, y, noise, bias, d, (__nv_bfloat16*)planes, (long long)n * hw * c, part_gb, part_gd,
+                                                            n, hw, c, slice, alpha, pool_w, gscale);
     int rc = launched("bwd_prep_planes");
     if (rc) return rc;
     const int blocks = (int)ceil_div(nc, 256);

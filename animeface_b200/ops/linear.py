@@ -35,8 +35,10 @@ def _fwd_raw(x, w, b, coef, gain, slope):
         raise RuntimeError(f'linear: input has {K} features, weight expects {w.shape[1]}')
     y = torch.empty((B, N), dtype=torch.float32, device=x.device)
     bb = None if b is None else _f32c(b.detach()).reshape(-1)
+    nbytes = int(lib.sg2_linear_fwd_workspace(B, K, N))
+    ws = torch.empty(nbytes // 4, dtype=torch.float32, device=x.device) if nbytes else None
     _lib.check(lib.sg2_linear_fwd(x.data_ptr(), w.data_ptr(), _lib.ptr(bb), y.data_ptr(), B, K, N, float(coef), float(gain),
-                                  float(1.0 if slope is None else slope), _lib.stream_ptr(x)), 'sg2_linear_fwd')
+                                  float(1.0 if slope is None else slope), _lib.ptr(ws), _lib.stream_ptr(x)), 'sg2_linear_fwd')
     return y
 
 

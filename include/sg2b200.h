@@ -240,9 +240,12 @@ int sg2_conv2d_wgrad_planes(const void* x_planes, const void* gy_planes, float* 
  *   bwd_weight: gw = coef * gu^T x,    gb = sum_b gu (gb may be NULL)
  * With bias = NULL, gain = 1, slope = 1, y = NULL the three calls are F(x,W) = x W^T, Dx(g,W) = g W, Dw(g,x) = g^T x:
  * a family closed under differentiation (what R1's double backward through the epilogue uses).  No atomics.
- *   pixelnorm:  y = x / (sqrt(mean_k x^2) + eps)                                                                  */
+ *   pixelnorm:  y = x / (sqrt(mean_k x^2) + eps)
+ * fwd splits a large K (the 8192-wide discriminator layer) over CTAs and adds the partial sums in a fixed order in a second
+ * pass: `workspace` = sg2_linear_fwd_workspace(B, K, N) bytes of device memory (0 bytes / NULL when K fits one slice).           */
+long long sg2_linear_fwd_workspace(int B, int K, int N);
 int sg2_linear_fwd(const float* x, const float* w, const float* bias, float* y, int B, int K, int N,
-                   float coef, float gain, float slope, sg2_stream_t stream);
+                   float coef, float gain, float slope, void* workspace, sg2_stream_t stream);
 int sg2_linear_bwd_data(const float* gy, const float* y, const float* w, float* gx, int B, int K, int N,
                         float coef, float gain, float slope, sg2_stream_t stream);
 int sg2_linear_bwd_weight(const float* gy, const float* y, const float* x, float* gw, float* gb, int B, int K, int N,
