@@ -382,11 +382,11 @@ def conv2d_bias_act(x, w, b, coef: float = 1.0, slope: float | None = 0.2, gain:
 # ----------------------------------------------------------------------------------------------
 # The whole residual discriminator block (DBlock.forward, implementations/StyleGAN2/model.py:204-212) as ONE autograd node:
 #   h1 = lrelu(conv3x3(x) + b1);  h2 = lrelu(conv3x3(h1) + b2);  t = conv1x1(x) + bs;  out = alpha * (avgpool2(h2) + avgpool2(t))
-# The forward is the same four launches as the separate ops.  What the single node buys is the first-order backward: the
-# pooling adjoint is folded into the two leaky-ReLU-gradient passes that follow it (the full-resolution gradient of the
-# pooling input is never written or read), x is split into planes once for the two weight gradients that consume it, and the
-# skip branch's data gradient accumulates in the epilogue of its kernel instead of a separate add.  Under create_graph (R1)
-# the backward is composed from the differentiable families, exactly like ConvBiasActFn.
+# What the single node buys: the skip branch runs at the pooled resolution (see forward), and in the first-order backward the
+# pooling adjoint is folded into the leaky-ReLU-gradient pass that follows it (the full-resolution gradient of the pooling
+# input is never written or read) and the two data gradients that meet at x accumulate in a kernel epilogue instead of a
+# separate add.  Under create_graph (R1) the backward is composed from the differentiable families, exactly like
+# ConvBiasActFn.
 
 def _composed_conv_backward(x, w, y, gy, coef, slope, need_gx, need_gw, need_gb):
     from .bias_act import act_grad
@@ -402,49 +402,66 @@ class DBlockFn(torch.autograd.Function):
     @amp_fwd
     def forward(ctx, x, w1, b1, w2, b2, ws, bs, coef1, coef2, coefs, slope, alpha):
         from .resample import _avgpool
+        n, ci, h, wd = x.shape
         h1 = _conv_raw(x, w1, coef1, False, bias=b1, slope=slope)
         h2 = _conv_raw(h1, w2, coef2, False, bias=b2, slope=slope)
-        t = _conv_raw(x, ws, coefs, False, bias=bs)
-        out = _avgpool(h2, t, alpha, False)
-        ctx.cfg = (coef1, coef2, coefs, slope, alpha)
-        ctx.save_for_backward(x, w1, w2, ws, h1, h2)
+        # The skip branch down(skip(x)) (model.py:207-211) is evaluated as skip(down(x)): a 1x1 convolution (+ bias) commutes with
+        # the 2x2 average that follows it, so the branch runs on a quarter of the pixels -- forward, data gradient and weight
+        # gradient -- and its full-resolution output t is never written.  Same function, different rounding order (~1e-7).
+        pooled_skip = h % 2 == 0 and wd % 2 == 0 and ci % 4 == 0
+        if pooled_skip:
+            xq = _avgpool(x, None, 1.0, False)
+            tq = _conv_raw(xq, ws, coefs, False, bias=bs)
+            out = _avgpool(h2, tq, alpha, False, t_pooled=True)
+        else:
+            xq = torch.empty(0, device=x.device)
+            out = _avgpool(h2, _conv_raw(x, ws, coefs, False, bias=bs), alpha, False)
+        ctx.cfg = (coef1, coef2, coefs, slope, alpha, pooled_skip)
+        ctx.save_for_backward(x, w1, w2, ws, h1, h2, xq)
         return out
 
     @staticmethod
     @amp_bwd
     def backward(ctx, g):
-        from .resample import AvgPool2AdjFn
-        x, w1, w2, ws, h1, h2 = ctx.saved_tensors
-        coef1, coef2, coefs, slope, alpha = ctx.cfg
+        from .resample import AvgPool2AdjFn, _avgpool
+        x, w1, w2, ws, h1, h2, xq = ctx.saved_tensors
+        coef1, coef2, coefs, slope, alpha, pooled_skip = ctx.cfg
         need = ctx.needs_input_grad
         n, ci, h, wd = x.shape
         co = w1.shape[0]
-        fast = (not torch.is_grad_enabled() and co % 4 == 0 and h % 2 == 0 and wd % 2 == 0
-                and _planes_ok(n, h, wd, co, ci, 3, False) and _planes_ok(n, h, wd, co, co, 3, False) and _planes_ok(n, h, wd, co, ci, 1, False)
-                and _planes_ok(n, h, wd, ci, co, 3, True) and _planes_ok(n, h, wd, co, co, 3, True) and _planes_ok(n, h, wd, ci, co, 1, True))
+        fast = (not torch.is_grad_enabled() and pooled_skip and co % 4 == 0
+                and _planes_ok(n, h, wd, co, ci, 3, False) and _planes_ok(n, h, wd, co, co, 3, False)
+                and _planes_ok(n, h, wd, ci, co, 3, True) and _planes_ok(n, h, wd, co, co, 3, True))
+        # the skip branch lives at the pooled resolution, which the planes kernels may not take (4 x 4 images): fp32-operand kernels then
+        skip_planes = _planes_ok(n, h // 2, wd // 2, co, ci, 1, False) and _planes_ok(n, h // 2, wd // 2, ci, co, 1, True)
         if not fast:
+            # composed from the differentiable families (create_graph, odd shapes): the gradient of the same function, written in
+            # the reference's order -- skip at full resolution, then the pooling adjoint
             gf = AvgPool2AdjFn.apply(g, alpha)
             gh1, gw2, gb2 = _composed_conv_backward(h1, w2, h2, gf, coef2, slope, True, need[3], need[4])
             gx1, gw1, gb1 = _composed_conv_backward(x, w1, h1, gh1, coef1, slope, need[0], need[1], need[2])
             gx2, gws, gbs = _composed_conv_backward(x, ws, None, gf, coefs, None, need[0], need[5], need[6])
             gx = gx1 + gx2 if need[0] else None
             return gx, gw1, gb1, gw2, gb2, gws, gbs, None, None, None, None, None
-        gscale = 0.25 * alpha
-        gu2p, gb2, _ = _bwd_prep_planes(g, h2, slope, pooled=True, gscale=gscale)          # d out / d h2, masked by lrelu'(h2)
-        gtp, gbs, _ = _bwd_prep_planes(g, None, None, pooled=True, gscale=gscale)           # d out / d t (no activation)
+        gu2p, gb2, _ = _bwd_prep_planes(g, h2, slope, pooled=True, gscale=0.25 * alpha)    # d out / d h2, masked by lrelu'(h2)
+        if skip_planes:
+            gtp, gbs, _ = _bwd_prep_planes(g, None, None, gscale=alpha)                     # d out / d tq, at the pooled resolution
+        else:
+            gt = g * alpha
+            gbs = gt.sum((0, 2, 3))
         gh1 = _conv_planes(gu2p, w2, coef2, True)
         gu1p, gb1, _ = _bwd_prep_planes(gh1, h1, slope)
         gx = None
         if need[0]:
-            gx = _conv_planes(gu1p, w1, coef1, True)
-            gx = _conv_planes(gtp, ws, coefs, True, accumulate_into=gx)
-        gw1 = gw2 = gws = None
-        if need[1] or need[5]:
-            xp = _split_planes(x)
-            gw1 = _wgrad_planes(xp, gu1p, 3, coef1) if need[1] else None
-            gws = _wgrad_planes(xp, gtp, 1, coefs) if need[5] else None
-        if need[3]:
-            gw2 = _wgrad_planes(_split_planes(h1), gu2p, 3, coef2)
+            # skip branch first: its data gradient at the pooled resolution, spread over the 2x2 windows (pooling adjoint) into
+            # gx; the main branch's data gradient then accumulates on top in the epilogue of its kernel
+            gxq = _conv_planes(gtp, ws, coefs, True) if skip_planes else _conv_raw(gt, ws, coefs, True)
+            gx = _conv_planes(gu1p, w1, coef1, True, accumulate_into=_avgpool(gxq, None, 1.0, True))
+        gw1 = _wgrad_planes(_split_planes(x), gu1p, 3, coef1) if need[1] else None
+        gws = None
+        if need[5]:
+            gws = _wgrad_planes(_split_planes(xq), gtp, 1, coefs) if skip_planes else _wgrad_raw(xq, gt, 1, coefs)
+        gw2 = _wgrad_planes(_split_planes(h1), gu2p, 3, coef2) if need[3] else None
         return (gx, gw1, gb1 if need[2] else None, gw2, gb2 if need[4] else None, gws, gbs if need[6] else None,
                 None, None, None, None, None)
 

@@ -81,9 +81,11 @@ int sg2_up2x_adj(const float* gy, float* gx, const float* scale,
 /* replaces: implementations/StyleGAN2/model.py:61-63 (AvgPool2d(2)) and the
  * residual merge (x + t)/sqrt(2) of DBlock.forward model.py:209-212.
  * y = alpha * (avg2x2(x) + (t ? avg2x2(t) : 0)).   x,t [n,h,w,c] NHWC dense, h,w even.
+ * t_pooled = 1: t is [n,h/2,w/2,c] and is added as it is, y = alpha * (avg2x2(x) + t) -- the skip branch of the block
+ *   computed at the pooled resolution (a 1x1 convolution commutes with the average pooling that follows it).
  * adj: gx = alpha * 0.25 * gy broadcast over each 2x2 window.                 */
 int sg2_avgpool2_fwd(const float* x, const float* t, float* y, float alpha,
-                     int n, int c, int h, int w, sg2_stream_t stream);
+                     int n, int c, int h, int w, int t_pooled, sg2_stream_t stream);
 int sg2_avgpool2_adj(const float* gy, float* gx, float alpha,
                      int n, int c, int h, int w, sg2_stream_t stream);
 
