@@ -220,7 +220,8 @@ extern "C" int sg2_bwd_prep_planes(const float* gy, const float* y, const float*
     int rc = launched("bwd_prep_planes");
     if (rc) return rc;
     const int blocks = (int)ceil_div(nc, 256);
-    sum_slices_kernel<<<blocks, 256, 0, st>>>(part_gb, gb, nc, (int)grid.z);
+    // gb: summed over the samples too (rows of the partial buffer are (slice, sample) pairs) -- the bias gradient, no torch pass
+    sum_slices_kernel<<<(unsigned)ceil_div(c, 256), 256, 0, st>>>(part_gb, gb, c, (int)grid.z * n);
     rc = launched("sum_slices");
     if (rc || !gd) return rc;
     sum_slices_kernel<<<blocks, 256, 0, st>>>(part_gd, gd, nc, (int)grid.z);

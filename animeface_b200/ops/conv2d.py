@@ -188,7 +188,7 @@ def _bwd_prep_planes(gy, y, slope, noise=None, bias=None, d=None, pooled=False, 
     gy = _cl(gy)
     yc = None if (slope is None and d is None) else _cl(y)      # y gives the leaky-ReLU sign and, for gd, the accumulator
     planes = torch.empty((2, n, h, wd, co), dtype=torch.bfloat16, device=gy.device)
-    gb = torch.empty((n, co), dtype=torch.float32, device=gy.device)
+    gb = torch.empty((co,), dtype=torch.float32, device=gy.device)
     gd = torch.empty((n, co), dtype=torch.float32, device=gy.device) if d is not None else None
     ws = _workspace(lib.sg2_bwd_prep_planes_workspace(n, h * wd, co), gy.device, 'sg2_bwd_prep_planes_workspace')
     f32 = lambda t: None if t is None else t.detach().to(torch.float32).contiguous()
@@ -197,7 +197,7 @@ def _bwd_prep_planes(gy, y, slope, noise=None, bias=None, d=None, pooled=False, 
                                        gb.data_ptr(), _lib.ptr(gd), ws.data_ptr(), n, h * wd, co,
                                        float(slope if slope is not None else 1.0), wd if pooled else 0, float(gscale),
                                        _lib.stream_ptr(gy)), 'sg2_bwd_prep_planes')
-    return planes, gb.sum(0), gd
+    return planes, gb, gd
 
 
 def _conv_planes(xp, w, coef, transpose, accumulate_into=None):

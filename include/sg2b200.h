@@ -206,7 +206,7 @@ int sg2_modconv_bwd_prep(const float* gy, const float* y, const float* noise, co
  *           are descriptor offsets into ONE tile.  bf16x3 arithmetic (~5e-6 relative), as impl 4.
  * sg2_split_planes:    planes = split(x * scale[b,c])   (scale may be NULL)                        c % 4 == 0
  * sg2_bwd_prep_planes: sg2_modconv_bwd_prep with g_acc written as planes and DETERMINISTIC per-(sample, channel) sums:
- *                      gb[n,c] = sum_hw gu, gd[n,c] = sum_hw gu * acc (NULL = skip); y NULL = no activation (gu = gy);
+ *                      gb[c] = sum_{n,hw} gu, gd[n,c] = sum_hw gu * acc (NULL = skip); y NULL = no activation (gu = gy);
  *                      workspace: sg2_bwd_prep_planes_workspace(n, hw, c) bytes.  pool_w > 0: gy is the gradient of the 2x2
  *                      average pooling that follows the layer (implementations/StyleGAN2/model.py:209-212), [n, hw/4, c] with
  *                      full-resolution width pool_w; its adjoint (broadcast * gscale) is applied on the fly.  gscale also
