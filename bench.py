@@ -315,7 +315,7 @@ def run_b200(args):
                     mma_per_product=3,
                     note='fp32 operands are split into two 16-bit planes (fp32-class results, DESIGN 3.1): every algorithmic '
                          'product costs 3 tensor-core MMAs, so the tensor pipe does 3x `achieved`; ncu tensor-pipe-active '
-                         'and DRAM bytes per launch: profiles/r1d_ncu_full_conv_wgrad.txt')
+                         'and DRAM bytes per launch: profiles/r2m_ncu_full.txt')
 
     # ---- end-to-end: host batch in pinned memory -> H2D each step, losses read back each step
     host = [torch.empty(B, 3, size, size, pin_memory=True).uniform_(-1, 1) for _ in range(2)]
