@@ -23,6 +23,7 @@ struct UpfirdnParams {
     float gain;
     int order[4];                    // dims of y sorted by decreasing stride (memory order)
     long long total;
+    int sepok;                       // ring walk: separable evaluation allowed (SG2_UPF_SEP=0 disables it: the A/B switch)
 };
 
 __device__ __forceinline__ int pos_mod(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
@@ -167,18 +168,21 @@ __global__ void __launch_bounds__(256) upfirdn2d_strip_nhwc(UpfirdnParams p) {
 // strip of STRIP output rows keeping the FH x FW input window in registers: going one row down costs DOWN x FW loads
 // instead of FH x FW -- each input element is fetched FW / DOWN times per thread-column instead of FH*FW / DOWN^2, and
 // neighbouring columns' fetches hit L1.  The strip loop is fully unrolled so the ring is addressed with constants.
+template <bool B> struct BoolTag { static constexpr bool value = B; };
 template <class V> struct RingVec;
 template <> struct RingVec<float4> {
     static __device__ __forceinline__ float4 zero() { return f4zero(); }
     static __device__ __forceinline__ float4 ld(const float* p) { return ldg4(p); }
     static __device__ __forceinline__ void st(float* p, const float4& v) { st4_cs(p, v); }
     static __device__ __forceinline__ void fma(float4& a, float s, const float4& v) { fma4(a, s, v); }
+    static __device__ __forceinline__ void fma_x2(float4& a, float s, const float4& v) { fma4_x2(a, s, v); }
 };
 template <> struct RingVec<float> {
     static __device__ __forceinline__ float zero() { return 0.f; }
     static __device__ __forceinline__ float ld(const float* p) { return __ldg(p); }
     static __device__ __forceinline__ void st(float* p, float v) { __stcs(p, v); }
     static __device__ __forceinline__ void fma(float& a, float s, float v) { a = fmaf(s, v, a); }
+    static __device__ __forceinline__ void fma_x2(float& a, float s, float v) { a = fmaf(s, v, a); }
 };
 
 template <class V, int FH, int FW, int DOWN, int COLS, int STRIP>
@@ -259,46 +263,89 @@ __global__ void __launch_bounds__(256) upfirdn2d_ring_kernel(UpfirdnParams p) {
     // memory-level parallelism, not by the FMAs.  Fully unrolled: every ring index is a constant.
     constexpr int NA = (FH + DOWN - 1) / DOWN;
     constexpr int NROWS = (STRIP - 1) * DOWN + FH;           // input rows a strip touches
+    // A rank-1 filter (setup_filter's outer product of a 1-D kernel: every blur of the path) is applied separably: the
+    // horizontal taps once per input row, then one FMA per output row the input row feeds -- COLS * (FW + NA) multiply-adds per
+    // input row instead of COLS * NA * FW.  Detected from the weights themselves (exact for the dyadic [1,3,3,1] family; a
+    // filter that is not recognised takes the general walk, same results to rounding).
+    bool sep = wt[0][0] != 0.f;
+#pragma unroll
+    for (int a = 0; a < FH; ++a)
+#pragma unroll
+        for (int b = 0; b < FW; ++b) {
+            const float lhs = wt[a][b] * wt[0][0], rhs = wt[a][0] * wt[0][b];
+            sep = sep && fabsf(lhs - rhs) <= 2.4e-7f * fabsf(rhs);
+        }
+    float fx[FW], fy[FH];
+#pragma unroll
+    for (int b = 0; b < FW; ++b) fx[b] = sep ? wt[0][b] / wt[0][0] : 0.f;
+#pragma unroll
+    for (int a = 0; a < FH; ++a) fy[a] = wt[a][0];
     V acc[NA][COLS];
 #pragma unroll
     for (int i = 0; i < NA; ++i)
 #pragma unroll
         for (int e = 0; e < COLS; ++e) acc[i][e] = R::zero();
+    // packed f32x2 FMAs in this walk: measured on B200 (U4 filter NHWC, fraction of HBM peak) general 0.54 -> 0.56,
+    // separable 0.59 -> 0.68; the input-stationary ring above keeps scalar FMAs (packed: 0.86 -> 0.70, its rotating window
+    // does not sit in aligned register pairs)
+    // (NCHW rows from three aligned 128-bit loads per 4 outputs instead of 7 scalar ones were tried: 0.57 -> 0.50 of HBM peak --
+    // 12 values fetched for 7 used, plus the selects that pick the window out of them)
+    auto walk = [&](auto separable) {
+        constexpr bool SEP = decltype(separable)::value;
+        auto fma = [](V& a, float s, const V& v) { R::fma_x2(a, s, v); };
 #pragma unroll
-    for (int k = 0; k < NROWS; ++k) {
-        V row[WW];
-        {
-            const int iy = iy0 + k;
-            const bool rowok = (unsigned)iy < (unsigned)p.in_h;
-            const float* xr = xc + (ptrdiff_t)iy * xrow;
+        for (int k = 0; k < NROWS; ++k) {
+            V row[WW];
+            {
+                const int iy = iy0 + k;
+                const bool rowok = (unsigned)iy < (unsigned)p.in_h;
+                const float* xr = xc + (ptrdiff_t)iy * xrow;
 #pragma unroll
-            for (int b = 0; b < WW; ++b) row[b] = (rowok && colok[b]) ? R::ld(xr + (ptrdiff_t)b * xcol) : R::zero();
-        }
+                for (int b = 0; b < WW; ++b) row[b] = (rowok && colok[b]) ? R::ld(xr + (ptrdiff_t)b * xcol) : R::zero();
+            }
+            V hrow[COLS];
+            if (SEP) {
 #pragma unroll
-        for (int a = 0; a < FH; ++a) {
-            // input row k is tap row a of output row s = (k - a) / DOWN
-            if ((k - a) >= 0 && (k - a) % DOWN == 0 && (k - a) / DOWN < STRIP) {
-                constexpr int dummy = 0; (void)dummy;
-                const int s = (k - a) / DOWN;
+                for (int e = 0; e < COLS; ++e) {
+                    hrow[e] = R::zero();
 #pragma unroll
-                for (int e = 0; e < COLS; ++e)
+                    for (int b = 0; b < FW; ++b) fma(hrow[e], fx[b], row[e * DOWN + b]);
+                }
+            }
 #pragma unroll
-                    for (int b = 0; b < FW; ++b) R::fma(acc[s % NA][e], wt[a][b], row[e * DOWN + b]);
-                if (a == FH - 1) {                           // last tap row of output s: store and recycle the accumulator
+            for (int a = 0; a < FH; ++a) {
+                // input row k is tap row a of output row s = (k - a) / DOWN
+                if ((k - a) >= 0 && (k - a) % DOWN == 0 && (k - a) / DOWN < STRIP) {
+                    const int s = (k - a) / DOWN;
 #pragma unroll
                     for (int e = 0; e < COLS; ++e) {
-                        if (jy0 + s < p.out_h && jx + e < p.out_w) R::st(y + (size_t)(jy0 + s) * yrow + (size_t)(jx + e) * ycol, acc[s % NA][e]);
-                        acc[s % NA][e] = R::zero();
+                        if (SEP) fma(acc[s % NA][e], fy[a], hrow[e]);
+                        else {
+#pragma unroll
+                            for (int b = 0; b < FW; ++b) fma(acc[s % NA][e], wt[a][b], row[e * DOWN + b]);
+                        }
+                    }
+                    if (a == FH - 1) {                           // last tap row of output s: store and recycle the accumulator
+#pragma unroll
+                        for (int e = 0; e < COLS; ++e) {
+                            if (jy0 + s < p.out_h && jx + e < p.out_w) R::st(y + (size_t)(jy0 + s) * yrow + (size_t)(jx + e) * ycol, acc[s % NA][e]);
+                            acc[s % NA][e] = R::zero();
+                        }
                     }
                 }
             }
         }
-    }
+    };
+    if (sep && p.sepok) walk(BoolTag<true>{}); else walk(BoolTag<false>{});
 }
 
 template <class V, int FH, int FW, int DOWN, int COLS, int STRIP>
-static int launch_ring_strip(const UpfirdnParams& p, cudaStream_t st) {
+static int launch_ring_strip(const UpfirdnParams& p_in, cudaStream_t st) {
     constexpr bool NHWC = sizeof(V) == 16;
+    static int sepok = -1;
+    if (sepok < 0) { const char* e = getenv("SG2_UPF_SEP"); sepok = e ? atoi(e) != 0 : 1; }
+    UpfirdnParams p = p_in;
+    p.sepok = sepok;
     dim3 grid;
     if (NHWC) grid = dim3((unsigned)ceil_div(ceil_div(p.out_w, COLS), 256 / (p.c / 4)), (unsigned)ceil_div(p.out_h, STRIP), (unsigned)p.n);
     else grid = dim3((unsigned)ceil_div(ceil_div(p.out_w, COLS) * ceil_div(p.out_h, STRIP), 256), 1u, (unsigned)(p.n * p.c));
@@ -324,12 +371,12 @@ template <class V, int FH, int FW, int DOWN>
 static int launch_ring(const UpfirdnParams& p, cudaStream_t st) {
     // NHWC: a thread = one pixel column x 4 channels.  NCHW: COLS adjacent columns of one plane.
     if constexpr (sizeof(V) == 16) {
-        // adjacent pixels per thread: with 1 every input pixel is fetched FW times through L1 (4 x the data for the 4x4 blur:
-        // ~92 B/clk/SM of L1 traffic at HBM speed, next to the 128 B/clk the L1 delivers); 2 pixels share a 5-wide window
-        // (2.5 x).  SG2_UPF_COLS_NHWC overrides the choice for the sweep (profiles/r2k_upfirdn_cols.txt).
+        // adjacent pixels per thread: with 1 every input pixel is fetched FW times through L1 (4 x the data for the 4x4 blur);
+        // 4 pixels share a 7-wide window (1.75 x).  Measured on B200 with the separable walk (U4 filter, fraction of HBM peak):
+        // 1 -> 0.68, 2 -> 0.69, 4 -> 0.73; the decimating form keeps 1 (0.86; 2 -> 0.71, 4 -> 0.31).  SG2_UPF_COLS_NHWC overrides.
         static int cols = 0;
         if (!cols) { const char* e = getenv("SG2_UPF_COLS_NHWC"); cols = e ? atoi(e) : -1; }
-        const int use = cols > 0 ? cols : (DOWN == 1 ? 2 : 1);
+        const int use = cols > 0 ? cols : (DOWN == 1 ? 4 : 1);
         if (use == 4) return launch_ring_cols<V, FH, FW, DOWN, 4>(p, st);
         if (use == 2) return launch_ring_cols<V, FH, FW, DOWN, 2>(p, st);
         return launch_ring_cols<V, FH, FW, DOWN, 1>(p, st);
