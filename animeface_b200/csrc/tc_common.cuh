@@ -19,6 +19,8 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// (a suspend-time hint on try_wait -- the hardware parks the thread instead of polling -- was measured: the polling goes away but
+// every hand-over wakes later; forward convs 3-5 % slower, step 50.3 -> 52.3 ms.  Plain polling stays.)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
