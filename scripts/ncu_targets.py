@@ -6,7 +6,8 @@ Each target launches its kernel twice (ncu profiles both; read the second).  Tar
   mod<L>                           the MODULATED forward: style scale on the activation tile, demodulation + bias + noise +
                                    leaky-ReLU in the epilogue (what north_star calls modulated_conv2d)
   dgradpl<L> / wgradpl<L>          bf16 pair-planes kernels of the first-order backward (conv_halo_pl.cu, wgrad_pl.cu)
-  prep64 / split64                 planes producers (planes.cu) on [32,64,256,256]
+  prep64 / preppool64 / split64    planes producers (planes.cu) on [32,64,256,256] (preppool: the pooling adjoint folded in)
+  fwdk1                            1x1 forward conv 32->64 @256^2 (staged TMA-store epilogue)
   up2x_fwd / up2x_adj / avgpool    StyleGAN2 resampling (resample_sg2.cu) at U1 / U3
   u4_nhwc / u4_nchw / u4_down2     upfirdn2d register-ring kernel (upfirdn2d.cu) at U4
   bias_act / mbstd / diffaug       bias_act_vec4 on [32,64,256,256], minibatch-stddev on [32,512,4,4], DiffAugment on [32,3,256,256]"""
@@ -26,7 +27,7 @@ DEV, B = 'cuda', 32
 SHAPES = {'64': (64, 64, 256), '128': (128, 128, 128), '256': (256, 256, 64), '512': (512, 512, 32), '32': (32, 64, 256),
           '64x32': (64, 32, 256), '32x32': (32, 32, 256)}
 DEFAULT = ['mod64x32', 'mod32x32', 'mod128', 'fwd64', 'fwd128', 'dgradpl64', 'dgradpl128', 'wgradpl64', 'wgradpl128', 'wgradpl512',
-           'prep64', 'split64', 'up2x_fwd', 'up2x_adj', 'avgpool', 'u4_nhwc', 'u4_nchw', 'u4_down2', 'bias_act', 'mbstd', 'diffaug']
+           'prep64', 'preppool64', 'split64', 'fwdk1', 'up2x_fwd', 'up2x_adj', 'avgpool', 'u4_nhwc', 'u4_nchw', 'u4_down2', 'bias_act', 'mbstd', 'diffaug']
 
 
 def cl(*shape):
@@ -64,6 +65,9 @@ def main():
             elif name in ('prep64', 'split64'):
                 gy, y = cl(B, 64, 256, 256), cl(B, 64, 256, 256)
                 twice((lambda: C._bwd_prep_planes(gy, y, 0.2)) if name == 'prep64' else (lambda: C._split_planes(gy)))
+            elif name == 'preppool64':
+                gp, y = cl(B, 64, 128, 128), cl(B, 64, 256, 256)
+                twice(lambda: C._bwd_prep_planes(gp, y, 0.2, pooled=True, gscale=0.2))
             elif name == 'fwdk1':
                 x, w1 = cl(B, 32, 256, 256), torch.randn(64, 32, 1, 1, device=DEV)
                 bias = torch.randn(64, device=DEV)
