@@ -232,6 +232,25 @@ int sg2_conv2d_wgrad_planes(const void* x_planes, const void* gy_planes, float* 
                             int n, int h, int w, int ci, int co, int k, float coef, int accumulate,
                             sg2_stream_t stream);
 
+/* filtered_lrelu ------------------------------------------------------------- *
+ * replaces: thirdparty/stylegan3_ops/ops/filtered_lrelu.py:50-268 (plugin entry filtered_lrelu.cpp:17, kernels
+ *           filtered_lrelu.cu:133-1093), called from implementations/StyleGAN3/model.py:186-190:
+ *             z = up^2 * FIR_fu(zero-insert(x + b[c], up), padded);  a = clamp(lrelu_slope(z) * gain);  y = decimate_down(FIR_fd(a))
+ *           as ONE kernel: a CTA keeps the input tile, the up-sampled intermediates and the activation in shared memory.
+ * x [planes = N*C][in_h][in_w] -> y [planes][out_h][out_w], dense NCHW fp32.  The "z grid" (zh x zw) is the up-sampled,
+ * fu-filtered signal: zw = in_w*up + padx0 + padx1 - (fu_n - 1).  Filters are given ORIENTED FOR CORRELATION (the caller
+ * flips them as upfirdn2d's flip_filter says): z[u] = up_gain * sum_t fu[t] xup[u + t] with xup[q] = x[(q - pad0)/up] where
+ * divisible, y[o] = sum_s fd[s] a[o*down + s + doff].  fu: fu_n taps applied along both axes, or fu_n x fu_n (fu_2d = 1); fd:
+ * fd_n taps (separable) or fd_n x fd_n (fd_2d = 1).
+ * mode 0: activation.  mode 1: activation, and mask[planes][zh][zw] (bytes) receives 0 (z <= 0), 1 (z > 0) or 2 (clamped).
+ * mode 2: a = z * gain * {slope, 1, 0}[mask] instead of the activation -- with x = dy, the flipped filters in swapped roles,
+ *   up <-> down, pad0 = fd_n - 1, doff = pad0_fwd - (fu_n - 1), up_gain = 1 and gain = gain_fwd * up_fwd^2 this is the
+ *   gradient w.r.t. x on the SAME z grid (the reference re-pads and offsets its sign tensor instead, filtered_lrelu.py:236-247). */
+int sg2_filtered_lrelu(const float* x, const float* b, float* y, void* mask, const float* fu, const float* fd, int fu_2d, int fd_2d,
+                       int planes, int channels, int in_h, int in_w, int up, int pad0x, int pad0y, int zh, int zw,
+                       int fu_n, int fd_n, int down, int doffx, int doffy, int out_h, int out_w,
+                       float up_gain, float gain, float slope, float clamp, int mode, sg2_stream_t stream);
+
 /* fully connected layers ------------------------------------------------------ *
  * replaces: nn.Linear inside ELR (implementations/StyleGAN2/model.py:29-37, 44-47) = ATen addmm (cuBLAS) -- the 8
  *           MapLinear + LeakyReLU of Mapping (:71-78, 263-282), ModulatedConv2d.affine (:102, 110), the discriminator
