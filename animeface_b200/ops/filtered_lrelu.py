@@ -5,13 +5,14 @@ decimation by `down`: the alias-suppressed non-linearity of the StyleGAN3 genera
 
 Two executions of the same arithmetic (the reference's ``_filtered_lrelu_ref``, :121-147):
 
-* **fused** (``csrc/filtered_lrelu.cu``, one launch): dense NCHW fp32 tensors, a 1-D (separable) ``fu`` and a 1-D or 2-D ``fd``.
+* **fused** (``csrc/filtered_lrelu.cu``, one launch): fp32 CUDA tensors (repacked to dense NCHW when they are not), a 1-D
+  (separable) ``fu`` and a 1-D or 2-D ``fd``.
   The up-sampled intermediates live in shared memory; when a backward will follow, one byte per up-sampled element records
   the sign / clamp state.  The backward is the SAME kernel reading that mask instead of applying the activation, with the
   filters in swapped roles -- the construction of the reference's ``FilteredLReluCuda.backward`` (:221-252), re-derived on the
   forward's own up-sampled grid; a 2-D ``fd`` (the radial filters) becomes the 2-D first stage of that launch.
-* **composed** (``bias_act`` / ``upfirdn2d`` launches, the up-sampled tensor materialised): everything else -- other layouts
-  and dtypes, a 2-D ``fu``, and any backward under ``create_graph`` (gradients of any order exist through the ops' own
+* **composed** (``bias_act`` / ``upfirdn2d`` launches, the up-sampled tensor materialised): everything else -- other dtypes,
+  a 2-D ``fu``, and any backward under ``create_graph`` (gradients of any order exist through the ops' own
   closed families).
 """
 from __future__ import annotations
@@ -59,7 +60,7 @@ def _launch(x, b, y, mask, fu_c, fd_c, up, pad0, z_hw, down, doff, up_gain, gain
 
 
 def _fusable(x, fu, fd, b):
-    if not (fused_enabled and x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.numel() > 0):
+    if not (fused_enabled and x.is_cuda and x.dtype == torch.float32 and x.numel() > 0):
         return False
     if fu is not None and (fu.ndim != 1 or fu.shape[0] > 64):
         return False
@@ -141,7 +142,9 @@ def filtered_lrelu(x, fu=None, fd=None, b=None, up=1, down=1, padding=0, gain=np
     out_w = (in_w * up + (px0 + px1) - (fu_w - 1) - (fd_w - 1) + (down - 1)) // down
     out_h = (in_h * up + (py0 + py1) - (fu_h - 1) - (fd_h - 1) + (down - 1)) // down
     if _fusable(x, fu, fd, b):
-        y = FilteredLReluFn.apply(x, b, fu, fd, up, down, pads, float(gain), float(slope), None if clamp is None else float(clamp), bool(flip_filter))
+        # the kernel walks (sample, channel) planes: a channels_last or cropped input is repacked first (one pass over the SMALL tensor;
+        # the composed form would write and re-read the up^2-times larger intermediates instead)
+        y = FilteredLReluFn.apply(x.contiguous(), b, fu, fd, up, down, pads, float(gain), float(slope), None if clamp is None else float(clamp), bool(flip_filter))
     else:
         y = _composed(x, fu, fd, b, up, down, pads, gain, slope, clamp, flip_filter)
     assert tuple(y.shape) == (n, c, out_h, out_w), (tuple(y.shape), (n, c, out_h, out_w))
