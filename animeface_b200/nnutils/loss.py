@@ -9,6 +9,8 @@ animeface_b200.model.Discriminator is twice differentiable on the library kernel
 """
 from __future__ import annotations
 
+import contextlib
+
 import torch
 import torch.nn.functional as F
 
@@ -70,8 +72,14 @@ def calc_grad(outputs, inputs, scaler=None):
         if _is_scaler(scaler):
             outputs = scaler.scale(outputs)
         ones = torch.ones(outputs.size(), device=outputs.device)
-        gradients = torch.autograd.grad(outputs=outputs, inputs=inputs, grad_outputs=ones,
-                                        create_graph=True, retain_graph=True, only_inputs=True)[0]
+        # only the gradient of `inputs` (an image or a latent) is wanted: the convolution nodes skip their weight gradients, as
+        # ATen's own convolution does for outputs nobody asked for (ops.conv2d.skip_weight_grads)
+        from ..ops.conv2d import skip_weight_grads
+        wanted = inputs if isinstance(inputs, (list, tuple)) else [inputs]
+        skip = not any(isinstance(t, torch.nn.Parameter) for t in wanted)
+        with (skip_weight_grads() if skip else contextlib.nullcontext()):
+            gradients = torch.autograd.grad(outputs=outputs, inputs=inputs, grad_outputs=ones,
+                                            create_graph=True, retain_graph=True, only_inputs=True)[0]
         if _is_scaler(scaler):
             gradients = gradients / scaler.get_scale()
     return gradients

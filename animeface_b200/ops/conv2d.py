@@ -237,6 +237,31 @@ def _wgrad_planes(xp, gyp, k, coef):
 # ----------------------------------------------------------------------------------------------
 # The closed family (any-order autograd).  `coef` is the ELR constant folded into the weight.
 
+_skip_weight_grads = False
+
+
+class skip_weight_grads:
+    """Inside this context the backward of every convolution node returns None for its weight: ``torch.autograd.grad(outputs,
+    inputs=image, create_graph=True)`` -- the first-order pass of R1 / path length (nnutils/loss/penalty.py:11-26) -- asks for
+    the gradient of the IMAGE only, but a custom Function cannot see that and would launch (and record for double backward)
+    every weight-gradient convolution of the discriminator just to have it discarded; ATen's native convolution skips them
+    through `task_should_compute_output`.  The second-order terms still reach the weights through Conv2dTransposeFn.backward.
+    A process-wide flag (autograd runs CUDA nodes on its own thread), like conv2d_gradfix.weight_gradients_disabled."""
+
+    def __enter__(self):
+        global _skip_weight_grads
+        self._prev, _skip_weight_grads = _skip_weight_grads, True
+        return self
+
+    def __exit__(self, *exc):
+        global _skip_weight_grads
+        _skip_weight_grads = self._prev
+
+
+def _need_gw(flag):
+    return flag and not _skip_weight_grads
+
+
 class Conv2dFn(torch.autograd.Function):
     """y = conv2d(x, w * coef), stride 1, same padding."""
 
@@ -254,7 +279,7 @@ class Conv2dFn(torch.autograd.Function):
         gx = gw = None
         if ctx.needs_input_grad[0]:
             gx = Conv2dTransposeFn.apply(gy, w, ctx.coef)
-        if ctx.needs_input_grad[1]:
+        if _need_gw(ctx.needs_input_grad[1]):
             gw = Conv2dWgradFn.apply(x, gy, w.shape[2], ctx.coef)
         return gx, gw, None, None
 
@@ -276,7 +301,7 @@ class Conv2dTransposeFn(torch.autograd.Function):
         ggy = gw = None
         if ctx.needs_input_grad[0]:
             ggy = Conv2dFn.apply(g, w, ctx.coef, False)       # a gradient quantity: bf16x3 is enough
-        if ctx.needs_input_grad[1]:
+        if _need_gw(ctx.needs_input_grad[1]):
             gw = Conv2dWgradFn.apply(g, gy, w.shape[2], ctx.coef)
         return ggy, gw, None
 
@@ -366,7 +391,7 @@ class ConvBiasActFn(torch.autograd.Function):
         gx = gw = None
         if ctx.needs_input_grad[0]:
             gx = Conv2dTransposeFn.apply(gu, w, ctx.coef)
-        if ctx.needs_input_grad[1]:
+        if _need_gw(ctx.needs_input_grad[1]):
             gw = Conv2dWgradFn.apply(x, gu, w.shape[2], ctx.coef)
         return gx, gw, (gb if ctx.needs_input_grad[2] else None), None, None, None
 
@@ -438,9 +463,9 @@ class DBlockFn(torch.autograd.Function):
             # composed from the differentiable families (create_graph, odd shapes): the gradient of the same function, written in
             # the reference's order -- skip at full resolution, then the pooling adjoint
             gf = AvgPool2AdjFn.apply(g, alpha)
-            gh1, gw2, gb2 = _composed_conv_backward(h1, w2, h2, gf, coef2, slope, True, need[3], need[4])
-            gx1, gw1, gb1 = _composed_conv_backward(x, w1, h1, gh1, coef1, slope, need[0], need[1], need[2])
-            gx2, gws, gbs = _composed_conv_backward(x, ws, None, gf, coefs, None, need[0], need[5], need[6])
+            gh1, gw2, gb2 = _composed_conv_backward(h1, w2, h2, gf, coef2, slope, True, _need_gw(need[3]), need[4])
+            gx1, gw1, gb1 = _composed_conv_backward(x, w1, h1, gh1, coef1, slope, need[0], _need_gw(need[1]), need[2])
+            gx2, gws, gbs = _composed_conv_backward(x, ws, None, gf, coefs, None, need[0], _need_gw(need[5]), need[6])
             gx = gx1 + gx2 if need[0] else None
             return gx, gw1, gb1, gw2, gb2, gws, gbs, None, None, None, None, None
         gu2p, gb2, _ = _bwd_prep_planes(g, h2, slope, pooled=True, gscale=0.25 * alpha)    # d out / d h2, masked by lrelu'(h2)
