@@ -182,9 +182,22 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
     const size_t off = ((size_t)tile * 128 + c_o % mt) * ncols + dxi * 64 + c_i % 64;
     const size_t split_stride = (size_t)tiles * 128 * ncols;
     float s = 0.f;
-    for (int sp = 0; sp < splits; ++sp) {
+    // the low-channel layers have few tiles and up to ~100 pixel splits: 8 splits of loads in flight (the sum keeps its order)
+    const size_t lo_off = stack ? (size_t)64 * ncols : 0;
+    int sp = 0;
+    for (; sp + 8 <= splits; sp += 8) {
+        float v[8], u[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            v[j] = __ldg(ws + (sp + j) * split_stride + off);
+            u[j] = stack ? __ldg(ws + (sp + j) * split_stride + off + lo_off) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[j] + u[j];
+    }
+    for (; sp < splits; ++sp) {
         float v = ws[sp * split_stride + off];
-        if (stack) v += ws[sp * split_stride + off + (size_t)64 * ncols];
+        if (stack) v += ws[sp * split_stride + off + lo_off];
         s += v;
     }
     s *= coef;
