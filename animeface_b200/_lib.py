@@ -32,7 +32,7 @@ SIGNATURES = {
                              _int, _int, _int, _int, _int, _int, _int, _int, _int, _int, _int, _f, _vp]),
     'sg2_up2x_fwd': (_int, [_vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _vp]),
     'sg2_up2x_adj': (_int, [_vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _vp]),
-    'sg2_avgpool2_fwd': (_int, [_vp, _vp, _vp, _f, _int, _int, _int, _int, _int, _vp]),
+    'sg2_avgpool2_fwd': (_int, [_vp, _vp, _vp, _vp, _f, _int, _int, _int, _int, _int, _vp]),
     'sg2_avgpool2_adj': (_int, [_vp, _vp, _f, _int, _int, _int, _int, _vp]),
     'sg2_bias_act': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _i64, _int, _i64, _int, _int, _f, _f, _f, _vp]),
     'sg2_mbstd_fwd': (_int, [_vp, _i64p, _vp, _i64p, _vp, _int, _int, _int, _int, _int, _f, _vp]),
@@ -50,7 +50,7 @@ SIGNATURES = {
     'sg2_modconv_bwd_prep': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _f, _vp, _vp]),
     'sg2_split_planes': (_int, [_vp, _vp, _vp, _int, _int, _int, _vp]),
     'sg2_bwd_prep_planes_workspace': (_i64, [_int, _int, _int]),
-    'sg2_bwd_prep_planes': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _f, _int, _f, _vp]),
+    'sg2_bwd_prep_planes': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _f, _int, _f, _vp]),
     'sg2_conv2d_planes_supported': (_int, [_int, _int, _int, _int, _int, _int, _int]),
     'sg2_conv2d_fwd_planes': (_int, [_vp, _vp, _vp, _i64p, _int, _int, _int, _int, _int, _int, _vp, _vp, _int, _f, _f, _int, _vp]),
     'sg2_conv2d_wgrad_planes_workspace': (_i64, [_int, _int, _int, _int, _int, _int]),

@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(256) bwd_prep_planes_kernel(const float* __res
                                                               const float* __restrict__ noise, const float* __restrict__ bias,
                                                               const float* __restrict__ d, __nv_bfloat16* __restrict__ planes,
                                                               long long plane_stride, float* __restrict__ part_gb, float* __restrict__ part_gd,
+                                                              const unsigned short* __restrict__ signs,
                                                               int n, int hw, int c, int slice, float alpha, int pool_w, float gscale) {
     __shared__ float sh[64 * 36];                          // rows x (CW + 4): 16 x 68 or 32 x 36
     const int cw = chunk_width(c), tpp = cw >> 2, rows = 256 / tpp;
@@ -123,6 +124,24 @@ __global__ void __launch_bounds__(256) bwd_prep_planes_kernel(const float* __res
                 const float4 g = scale4(ldg4(gy + gbase + (long long)i * c), gscale);
                 const int p00 = (2 * py) * pool_w + 2 * px;
                 const int pix[4] = {p00, p00 + 1, p00 + pool_w, p00 + pool_w + 1};
+                if (signs) {
+                    // the window's leaky-ReLU signs from the 16-bit word the pooling kernel wrote (sg2_avgpool2_fwd): y is not read
+                    const unsigned m = signs[(gbase + (long long)i * c) >> 2];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const unsigned b4 = m >> (4 * e);
+                        float4 gu;
+                        gu.x = (b4 & 1) ? g.x : g.x * alpha; gu.y = (b4 & 2) ? g.y : g.y * alpha;
+                        gu.z = (b4 & 4) ? g.z : g.z * alpha; gu.w = (b4 & 8) ? g.w : g.w * alpha;
+                        const long long o = base + (long long)pix[e] * c;
+                        uint2 hi, lo;
+                        split4(mul4(gu, dv), hi, lo);
+                        *reinterpret_cast<uint2*>(planes + o) = hi;
+                        *reinterpret_cast<uint2*>(planes + plane_stride + o) = lo;
+                        sgu = add4(sgu, gu);
+                    }
+                    continue;
+                }
                 float4 yv[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) yv[e] = y ? ldg4(y + base + (long long)pix[e] * c) : f4zero();
@@ -197,12 +216,13 @@ extern "C" int64_t sg2_bwd_prep_planes_workspace(int n, int hw, int c) {
 }
 
 extern "C" int sg2_bwd_prep_planes(const float* gy, const float* y, const float* noise, const float* bias, const float* d,
-                                   void* planes, float* gb, float* gd, void* workspace,
+                                   void* planes, float* gb, float* gd, void* workspace, const void* signs,
                                    int n, int hw, int c, float alpha, int pool_w, float gscale, sg2_stream_t stream) {
     SG2_REQUIRE(gy && planes && gb && workspace, "bwd_prep_planes: null pointer");
     SG2_REQUIRE(n > 0 && hw > 0 && c > 0 && c % 4 == 0, "bwd_prep_planes: need n,hw > 0 and C %% 4 == 0 (C=%d)", c);
     SG2_REQUIRE(alpha != 0.f, "bwd_prep_planes: alpha must be non-zero (the activation is inverted from y)");
     SG2_REQUIRE(!gd || (d && y), "bwd_prep_planes: gd requested without d / y");
+    SG2_REQUIRE(!signs || (pool_w > 0 && !gd && !y), "bwd_prep_planes: window signs replace y in the pooled form only (no gd)");
     SG2_REQUIRE(pool_w == 0 || (pool_w > 0 && pool_w % 2 == 0 && hw % pool_w == 0 && (hw / pool_w) % 2 == 0),
                 "bwd_prep_planes: pooled gradient needs an even full-resolution width and height (w=%d, hw=%d)", pool_w, hw);
     cudaStream_t st = (cudaStream_t)stream;
@@ -213,10 +233,10 @@ extern "C" int sg2_bwd_prep_planes(const float* gy, const float* y, const float*
     float* part_gd = gd ? part_gb + (long long)grid.z * nc : nullptr;
     if (pool_w > 0)
         bwd_prep_planes_kernel<true><<<grid, 256, 0, st>>>(gy, y, noise, bias, d, (__nv_bfloat16*)planes, (long long)n * hw * c, part_gb, part_gd,
-                                                           n, hw, c, slice, alpha, pool_w, gscale);
+                                                           (const unsigned short*)signs, n, hw, c, slice, alpha, pool_w, gscale);
     else
         bwd_prep_planes_kernel<false><<<grid, 256, 0, st>>>(gy, y, noise, bias, d, (__nv_bfloat16*)planes, (long long)n * hw * c, part_gb, part_gd,
-                                                            n, hw, c, slice, alpha, pool_w, gscale);
+                                                            nullptr, n, hw, c, slice, alpha, pool_w, gscale);
     int rc = launched("bwd_prep_planes");
     if (rc) return rc;
     const int blocks = (int)ceil_div(nc, 256);

@@ -256,8 +256,11 @@ __global__ void __launch_bounds__(256) up2x_adj_strip_kernel(const float* __rest
 
 // y = alpha * (avg2x2(x) + avg2x2(t)),  NHWC, one thread = one output pixel x 4 channels.
 // t_pooled: t already has the output resolution and is added as it is: y = alpha * (avg2x2(x) + t).
+// signs (optional): one uint16 per (output pixel, 4-channel group) = the signs (x > 0) of the 2x2 window, bit 4*p + e for window
+// pixel p (row-major) and channel e -- what the leaky-ReLU gradient pass of the layer that produced x needs of it (planes.cu).
 __global__ void __launch_bounds__(256) avgpool2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ t,
-                                                           float* __restrict__ y, float alpha, int n, int c, int h, int w, int t_pooled) {
+                                                           float* __restrict__ y, unsigned short* __restrict__ signs, float alpha,
+                                                           int n, int c, int h, int w, int t_pooled) {
     const int cq = c >> 2, oh = h >> 1, ow = w >> 1;
     const long long total = (long long)n * oh * ow * cq;
     const float k = 0.25f * alpha;
@@ -270,8 +273,13 @@ __global__ void __launch_bounds__(256) avgpool2_fwd_kernel(const float* __restri
         int b = (int)(r / oh);
         const long long base = (((long long)b * h + 2 * oy) * w + 2 * ox) * c + 4 * q;
         const long long rs = (long long)w * c;
-        float4 a = add4(add4(ldg4(x + base), ldg4(x + base + c)), add4(ldg4(x + base + rs), ldg4(x + base + rs + c)));
+        const float4 x00 = ldg4(x + base), x01 = ldg4(x + base + c), x10 = ldg4(x + base + rs), x11 = ldg4(x + base + rs + c);
+        float4 a = add4(add4(x00, x01), add4(x10, x11));
         const long long o = (((long long)b * oh + oy) * ow + ox) * c + 4 * q;
+        if (signs) {
+            auto bits = [](const float4& v) { return (unsigned)(v.x > 0.f) | ((unsigned)(v.y > 0.f) << 1) | ((unsigned)(v.z > 0.f) << 2) | ((unsigned)(v.w > 0.f) << 3); };
+            signs[o >> 2] = (unsigned short)(bits(x00) | (bits(x01) << 4) | (bits(x10) << 8) | (bits(x11) << 12));
+        }
         if (t && !t_pooled) a = add4(a, add4(add4(ldg4(t + base), ldg4(t + base + c)), add4(ldg4(t + base + rs), ldg4(t + base + rs + c))));
         a = scale4(a, k);
         if (t && t_pooled) { const float4 tv = ldg4(t + o); a.x = fmaf(alpha, tv.x, a.x); a.y = fmaf(alpha, tv.y, a.y); a.z = fmaf(alpha, tv.z, a.z); a.w = fmaf(alpha, tv.w, a.w); }
@@ -349,14 +357,14 @@ extern "C" int sg2_up2x_adj(const float* gy, float* gx, const float* scale, int 
     return up2x_launch(true, gy, gx, scale, n, c, h, w, nhwc, blur, (cudaStream_t)stream);
 }
 
-extern "C" int sg2_avgpool2_fwd(const float* x, const float* t, float* y, float alpha,
+extern "C" int sg2_avgpool2_fwd(const float* x, const float* t, float* y, void* signs, float alpha,
                                 int n, int c, int h, int w, int t_pooled, sg2_stream_t stream) {
     SG2_REQUIRE(x && y, "avgpool2_fwd: null pointer");
     SG2_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, "avgpool2_fwd: h and w must be even and positive");
     SG2_REQUIRE(c % 4 == 0, "avgpool2_fwd: C %% 4 != 0 (C=%d)", c);
     const long long total = (long long)n * (h / 2) * (w / 2) * (c / 4);
     const int blocks = (int)std::min<long long>(ceil_div(total, 256), (long long)num_sms() * 16);
-    avgpool2_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, t, y, alpha, n, c, h, w, t_pooled);
+    avgpool2_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, t, y, (unsigned short*)signs, alpha, n, c, h, w, t_pooled);
     return launched("avgpool2_fwd");
 }
 

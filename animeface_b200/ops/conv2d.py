@@ -176,17 +176,19 @@ def _split_planes(x, scale=None):
     return planes
 
 
-def _bwd_prep_planes(gy, y, slope, noise=None, bias=None, d=None, pooled=False, gscale=1.0):
+def _bwd_prep_planes(gy, y, slope, noise=None, bias=None, d=None, pooled=False, gscale=1.0, signs=None):
     """One pass over (gy, y): gu = gy * lrelu'(y) (slope None: gu = gy, y is not read); returns (planes of gu * d, gb [co],
     gd [n,co] or None).  The per-(sample, channel) sums are reduced in a fixed order (deterministic).
     pooled: gy is the gradient of the 2x2 average pooling that follows the layer (half the resolution); its adjoint
-    (broadcast * gscale) is applied while reading."""
+    (broadcast * gscale) is applied while reading.  signs (pooled only): the window signs of y the pooling kernel wrote --
+    read instead of y."""
     lib = _lib.load()
     n, co, h, wd = gy.shape
     if pooled:
         h, wd = 2 * h, 2 * wd
     gy = _cl(gy)
-    yc = None if (slope is None and d is None) else _cl(y)      # y gives the leaky-ReLU sign and, for gd, the accumulator
+    yc = None if ((slope is None and d is None) or signs is not None) else _cl(y)      # y gives the leaky-ReLU sign and, for gd, the accumulator
+    assert signs is None or (pooled and d is None and slope is not None)
     planes = torch.empty((2, n, h, wd, co), dtype=torch.bfloat16, device=gy.device)
     gb = torch.empty((co,), dtype=torch.float32, device=gy.device)
     gd = torch.empty((n, co), dtype=torch.float32, device=gy.device) if d is not None else None
@@ -194,7 +196,7 @@ def _bwd_prep_planes(gy, y, slope, noise=None, bias=None, d=None, pooled=False, 
     f32 = lambda t: None if t is None else t.detach().to(torch.float32).contiguous()
     noise, bias, d = f32(noise), (None if bias is None else f32(bias).reshape(-1)), f32(d)
     _lib.check(lib.sg2_bwd_prep_planes(gy.data_ptr(), _lib.ptr(yc), _lib.ptr(noise), _lib.ptr(bias), _lib.ptr(d), planes.data_ptr(),
-                                       gb.data_ptr(), _lib.ptr(gd), ws.data_ptr(), n, h * wd, co,
+                                       gb.data_ptr(), _lib.ptr(gd), ws.data_ptr(), _lib.ptr(signs), n, h * wd, co,
                                        float(slope if slope is not None else 1.0), wd if pooled else 0, float(gscale),
                                        _lib.stream_ptr(gy)), 'sg2_bwd_prep_planes')
     return planes, gb, gd
@@ -437,19 +439,21 @@ class DBlockFn(torch.autograd.Function):
         if pooled_skip:
             xq = _avgpool(x, None, 1.0, False)
             tq = _conv_raw(xq, ws, coefs, False, bias=bs)
-            out = _avgpool(h2, tq, alpha, False, t_pooled=True)
+            # the pooling kernel reads h2 anyway: it also records the leaky-ReLU signs of every window (2 bytes per 16 elements), so
+            # the backward pass that follows the pooling adjoint reads those instead of h2 (64 bytes per window)
+            out, signs2 = _avgpool(h2, tq, alpha, False, t_pooled=True, want_signs=True)
         else:
-            xq = torch.empty(0, device=x.device)
+            xq = signs2 = torch.empty(0, device=x.device)
             out = _avgpool(h2, _conv_raw(x, ws, coefs, False, bias=bs), alpha, False)
         ctx.cfg = (coef1, coef2, coefs, slope, alpha, pooled_skip)
-        ctx.save_for_backward(x, w1, w2, ws, h1, h2, xq)
+        ctx.save_for_backward(x, w1, w2, ws, h1, h2, xq, signs2)
         return out
 
     @staticmethod
     @amp_bwd
     def backward(ctx, g):
         from .resample import AvgPool2AdjFn, _avgpool
-        x, w1, w2, ws, h1, h2, xq = ctx.saved_tensors
+        x, w1, w2, ws, h1, h2, xq, signs2 = ctx.saved_tensors
         coef1, coef2, coefs, slope, alpha, pooled_skip = ctx.cfg
         need = ctx.needs_input_grad
         n, ci, h, wd = x.shape
@@ -468,7 +472,8 @@ class DBlockFn(torch.autograd.Function):
             gx2, gws, gbs = _composed_conv_backward(x, ws, None, gf, coefs, None, need[0], _need_gw(need[5]), need[6])
             gx = gx1 + gx2 if need[0] else None
             return gx, gw1, gb1, gw2, gb2, gws, gbs, None, None, None, None, None
-        gu2p, gb2, _ = _bwd_prep_planes(g, h2, slope, pooled=True, gscale=0.25 * alpha)    # d out / d h2, masked by lrelu'(h2)
+        gu2p, gb2, _ = _bwd_prep_planes(g, h2, slope, pooled=True, gscale=0.25 * alpha,       # d out / d h2, masked by lrelu'(h2)
+                                        signs=signs2 if signs2.numel() else None)
         if skip_planes:
             gtp, gbs, _ = _bwd_prep_planes(g, None, None, gscale=alpha)                     # d out / d tq, at the pooled resolution
         else:

@@ -83,7 +83,7 @@ def upsample2x_bilinear(x):
     return Up2xFn.apply(x, False)
 
 
-def _avgpool(x, t, alpha, adjoint, t_pooled=False):
+def _avgpool(x, t, alpha, adjoint, t_pooled=False, want_signs=False):
     lib = _lib.load()
     _lib.require_cuda(x)
     n, c, h, w = x.shape
@@ -97,8 +97,11 @@ def _avgpool(x, t, alpha, adjoint, t_pooled=False):
         y = _empty_cl(n, c, h // 2, w // 2, x)
         if t is not None and tuple(t.shape) != ((n, c, h // 2, w // 2) if t_pooled else (n, c, h, w)):
             raise RuntimeError(f'avgpool2: residual input has shape {tuple(t.shape)}')
-        _lib.check(lib.sg2_avgpool2_fwd(x.data_ptr(), _lib.ptr(t), y.data_ptr(), float(alpha), n, c, h, w, 1 if t_pooled else 0,
-                                        _lib.stream_ptr(x)), 'sg2_avgpool2_fwd')
+        signs = torch.empty((n, h // 2, w // 2, c // 4), dtype=torch.int16, device=x.device) if want_signs else None
+        _lib.check(lib.sg2_avgpool2_fwd(x.data_ptr(), _lib.ptr(t), y.data_ptr(), _lib.ptr(signs), float(alpha), n, c, h, w,
+                                        1 if t_pooled else 0, _lib.stream_ptr(x)), 'sg2_avgpool2_fwd')
+        if want_signs:
+            return y, signs
     return y
 
 

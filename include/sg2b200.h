@@ -83,8 +83,10 @@ int sg2_up2x_adj(const float* gy, float* gx, const float* scale,
  * y = alpha * (avg2x2(x) + (t ? avg2x2(t) : 0)).   x,t [n,h,w,c] NHWC dense, h,w even.
  * t_pooled = 1: t is [n,h/2,w/2,c] and is added as it is, y = alpha * (avg2x2(x) + t) -- the skip branch of the block
  *   computed at the pooled resolution (a 1x1 convolution commutes with the average pooling that follows it).
+ * signs (may be NULL): [n,h/2,w/2,c/4] uint16, the signs (x > 0) of each 2x2 window x 4 channels (bit 4*pixel + channel) --
+ *   sg2_bwd_prep_planes reads them instead of x when it applies the leaky-ReLU gradient of the layer that produced x.
  * adj: gx = alpha * 0.25 * gy broadcast over each 2x2 window.                 */
-int sg2_avgpool2_fwd(const float* x, const float* t, float* y, float alpha,
+int sg2_avgpool2_fwd(const float* x, const float* t, float* y, void* signs, float alpha,
                      int n, int c, int h, int w, int t_pooled, sg2_stream_t stream);
 int sg2_avgpool2_adj(const float* gy, float* gx, float alpha,
                      int n, int c, int h, int w, sg2_stream_t stream);
@@ -210,7 +212,8 @@ int sg2_modconv_bwd_prep(const float* gy, const float* y, const float* noise, co
  *                      workspace: sg2_bwd_prep_planes_workspace(n, hw, c) bytes.  pool_w > 0: gy is the gradient of the 2x2
  *                      average pooling that follows the layer (implementations/StyleGAN2/model.py:209-212), [n, hw/4, c] with
  *                      full-resolution width pool_w; its adjoint (broadcast * gscale) is applied on the fly.  gscale also
- *                      scales an ordinary gy.  sg2_conv2d_fwd_planes(accumulate = 1) adds into y instead of overwriting it.
+ *                      scales an ordinary gy.  signs (pooled form, y = NULL): the window signs sg2_avgpool2_fwd wrote, read
+ *                      instead of y (2 bytes instead of 64 per window).  sg2_conv2d_fwd_planes(accumulate = 1) adds into y instead of overwriting it.
  * sg2_conv2d_fwd_planes: y = gain * act(out_scale * conv(x, w) + bias) with x given as planes [2][n,h,w,ci]
  *                      (ci % 64 == 0); packed_w from sg2_conv2d_pack_weight(impl = 4) -- with transpose = 1 this is the
  *                      data gradient.  sg2_conv2d_planes_supported(.., wgrad = 0) tells whether the shape is taken.
@@ -220,7 +223,7 @@ int sg2_modconv_bwd_prep(const float* gy, const float* y, const float* noise, co
 int sg2_split_planes(const float* x, const float* scale, void* planes, int n, int hw, int c, sg2_stream_t stream);
 int64_t sg2_bwd_prep_planes_workspace(int n, int hw, int c);
 int sg2_bwd_prep_planes(const float* gy, const float* y, const float* noise, const float* bias, const float* d,
-                        void* planes, float* gb, float* gd, void* workspace,
+                        void* planes, float* gb, float* gd, void* workspace, const void* signs,
                         int n, int hw, int c, float alpha, int pool_w, float gscale, sg2_stream_t stream);
 int sg2_conv2d_planes_supported(int n, int h, int w, int ci, int co, int k, int wgrad);
 int sg2_conv2d_fwd_planes(const void* x_planes, const void* packed_w, float* y, const int64_t y_strides[4],
