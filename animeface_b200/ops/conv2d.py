@@ -585,6 +585,41 @@ class ModConvFn(torch.autograd.Function):
         return gx, gw, gs, gd, (gb if b is not None else None), None, None, None, None
 
 
+class DemodFn(torch.autograd.Function):
+    """d[b,o] = rsqrt(coef^2 * sum_i s[b,i]^2 * sum_k w[o,i,k]^2 + eps) (model.py:118-120 on the [B,Co] coefficient), first order
+    (path-length steps, which differentiate twice through d, run the tensor expression inside any_order_modconv)."""
+
+    @staticmethod
+    @amp_fwd
+    def forward(ctx, w, s, coef, eps):
+        lib = _lib.load()
+        co, ci, k, _ = w.shape
+        w, s = w.contiguous(), s.contiguous()
+        B = s.shape[0]
+        wsq = torch.empty((co, ci), dtype=torch.float32, device=w.device)
+        d = torch.empty((B, co), dtype=torch.float32, device=w.device)
+        _lib.check(lib.sg2_demod_fwd(w.data_ptr(), s.data_ptr(), wsq.data_ptr(), d.data_ptr(), B, co, ci, k * k, float(coef), float(eps),
+                                     _lib.stream_ptr(w)), 'sg2_demod_fwd')
+        ctx.coef = coef
+        ctx.save_for_backward(w, s, wsq, d)
+        return d
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    @amp_bwd
+    def backward(ctx, gd):
+        lib = _lib.load()
+        w, s, wsq, d = ctx.saved_tensors
+        co, ci, k, _ = w.shape
+        B = s.shape[0]
+        gd = gd.to(torch.float32).contiguous()
+        gw = torch.empty_like(w) if ctx.needs_input_grad[0] else None
+        gs = torch.empty_like(s) if ctx.needs_input_grad[1] else None
+        _lib.check(lib.sg2_demod_bwd(w.data_ptr(), s.data_ptr(), wsq.data_ptr(), d.data_ptr(), gd.data_ptr(), _lib.ptr(gw), _lib.ptr(gs),
+                                     B, co, ci, k * k, float(ctx.coef), _lib.stream_ptr(w)), 'sg2_demod_bwd')
+        return gw, gs, None, None
+
+
 _any_order = False
 
 
@@ -628,8 +663,12 @@ def modulated_conv2d(x, w, s, bias=None, noise=None, demod=True, slope=None, eps
     coef = 1.0 / float(ci * k * k) ** 0.5
     d = None
     if demod:
-        wsq = w.square().sum((2, 3))                       # [Co,Ci]
-        d = torch.rsqrt(torch.matmul(s.square(), wsq.t()) * (coef * coef) + eps)
+        if (not _any_order and w.is_cuda and w.dtype == torch.float32 and s.dtype == torch.float32 and ci <= 2048 and co <= 2048
+                and s.shape[0] <= 256):
+            d = DemodFn.apply(w, s, coef, float(eps))          # one launch (two in the backward) instead of ~7 (~12)
+        else:
+            wsq = w.square().sum((2, 3))                       # [Co,Ci]
+            d = torch.rsqrt(torch.matmul(s.square(), wsq.t()) * (coef * coef) + eps)
     if in_gain is not None:
         # StyleGAN3's magnitude-EMA input gain (implementations/StyleGAN3/model.py:62-65): scales the weight per input channel
         # AFTER demodulation, i.e. it rides with the style on the activation tile but stays out of d

@@ -235,6 +235,17 @@ int sg2_conv2d_wgrad_planes(const void* x_planes, const void* gy_planes, float* 
                             int n, int h, int w, int ci, int co, int k, float coef, int accumulate,
                             sg2_stream_t stream);
 
+/* demodulation coefficient ----------------------------------------------------- *
+ * replaces: the tensor expression of implementations/StyleGAN2/model.py:115-120 reduced to the [B,Co] coefficient
+ *           d[b,o] = rsqrt(coef^2 * sum_i s[b,i]^2 * sum_k w[o,i,k]^2 + eps)   (pow, reduce, sgemm, mul, add, rsqrt)
+ *           and its autograd backward (two sgemms + elementwise): one launch forward, two backward.
+ * w [co][ci][kk], s [B][ci], wsq [co][ci] (written by fwd, read by bwd), d / gd [B][co]; gw [co][ci][kk] and gs [B][ci] may be
+ * NULL (skipped).  ci, co <= 2048, B <= 256.  No atomics.                                                                   */
+int sg2_demod_fwd(const float* w, const float* s, float* wsq, float* d, int B, int co, int ci, int kk, float coef, float eps,
+                  sg2_stream_t stream);
+int sg2_demod_bwd(const float* w, const float* s, const float* wsq, const float* d, const float* gd, float* gw, float* gs,
+                  int B, int co, int ci, int kk, float coef, sg2_stream_t stream);
+
 /* filtered_lrelu ------------------------------------------------------------- *
  * replaces: thirdparty/stylegan3_ops/ops/filtered_lrelu.py:50-268 (plugin entry filtered_lrelu.cpp:17, kernels
  *           filtered_lrelu.cu:133-1093), called from implementations/StyleGAN3/model.py:186-190:
