@@ -26,11 +26,10 @@ __global__ void __launch_bounds__(256) thin_in_kernel(ConvParams p) {
     for (int i = threadIdx.x; i < CIN * p.co; i += blockDim.x) sw[i] = ((const float*)p.wp)[i];
     __syncthreads();
     const int cq = p.co >> 2, hw = p.h * p.w;
-    const long long total = (long long)p.n * hw * cq;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int q = (int)(idx % cq);
-        const long long pix = idx / cq;
-        const int b = (int)(pix / hw);
+    const long long P = (long long)p.n * hw;
+    const bool per_sample = p.in_scale || p.out_scale;
+    auto pixel = [&](long long pix, int q) {
+        const int b = per_sample ? (int)(pix / hw) : 0;
         float4 acc = f4zero();
 #pragma unroll
         for (int c = 0; c < CIN; ++c) {
@@ -46,7 +45,19 @@ __global__ void __launch_bounds__(256) thin_in_kernel(ConvParams p) {
             acc.z = acc.z > 0.f ? acc.z : acc.z * p.alpha; acc.w = acc.w > 0.f ? acc.w : acc.w * p.alpha;
         }
         st4_cs(p.y + pix * p.co + 4 * q, scale4(acc, p.gain));     // y is dense NHWC (checked by the launcher)
+    };
+    if (256 % cq == 0) {
+        // the channel quad of a thread is fixed and its pixel advances by a constant: no division in the loop, two pixels in flight
+        const int q = threadIdx.x % cq, ppb = 256 / cq;
+        const long long step = (long long)gridDim.x * ppb;
+        long long pix = (long long)blockIdx.x * ppb + threadIdx.x / cq;
+        for (; pix + step < P; pix += 2 * step) { pixel(pix, q); pixel(pix + step, q); }
+        if (pix < P) pixel(pix, q);
+        return;
     }
+    const long long total = P * cq;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
+        pixel(idx / cq, (int)(idx % cq));
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -179,6 +179,33 @@ __global__ void __launch_bounds__(256) sum_slices_kernel(const float* __restrict
     out[i] = s;
 }
 
+// the same for MANY rows and few columns (the bias gradient: rows = slices x samples, up to a few thousand; columns = channels):
+// a block owns 32 columns, its 8 warps take every 8th row with 4 rows of loads in flight, and the 8 partial sums meet in
+// shared memory in warp order -- a fixed order, so the result is still run-to-run identical
+__global__ void __launch_bounds__(256) sum_rows_kernel(const float* __restrict__ part, float* __restrict__ out, int nc, int rows) {
+    __shared__ float sh[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
+    float s = 0.f;
+    if (i < nc) {
+        int k = warp;
+        for (; k + 24 < rows; k += 32) {
+            const float a = part[(long long)k * nc + i], b = part[(long long)(k + 8) * nc + i];
+            const float c = part[(long long)(k + 16) * nc + i], d = part[(long long)(k + 24) * nc + i];
+            s += a; s += b; s += c; s += d;
+        }
+        for (; k < rows; k += 8) s += part[(long long)k * nc + i];
+    }
+    sh[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0 && i < nc) {
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t += sh[j][lane];
+        out[i] = t;
+    }
+}
+
 static int host_chunk_width(int c) { return (c % 64 == 0 || c > 32) ? 64 : (c > 16 ? 32 : 16); }
 
 // `items` = pixels a thread walks (pooled pixels for the pooled prologue); the slice count is the same for both so that one
@@ -241,7 +268,7 @@ extern "C" int sg2_bwd_prep_planes(const float* gy, const float* y, const float*
     if (rc) return rc;
     const int blocks = (int)ceil_div(nc, 256);
     // gb: summed over the samples too (rows of the partial buffer are (slice, sample) pairs) -- the bias gradient, no torch pass
-    sum_slices_kernel<<<(unsigned)ceil_div(c, 256), 256, 0, st>>>(part_gb, gb, c, (int)grid.z * n);
+    sum_rows_kernel<<<(unsigned)ceil_div(c, 32), 256, 0, st>>>(part_gb, gb, c, (int)grid.z * n);
     rc = launched("sum_slices");
     if (rc || !gd) return rc;
     sum_slices_kernel<<<blocks, 256, 0, st>>>(part_gd, gd, nc, (int)grid.z);
