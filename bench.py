@@ -30,10 +30,10 @@ TOP_KERNEL = 'halo::conv_halo_kernel<128, 1> grid 148'      # largest single ker
 
 def load_traffic():
     """(DRAM bytes per launch of the step's largest kernel, the per-kernel table) from the committed `ncu --set full` capture
-    (profiles/r3_ncu_traffic.json, written by scripts/ncu_summary.py from the .ncu-rep of scripts/ncu_targets.py: full layer
+    (profiles/r4_ncu_traffic.json, written by scripts/ncu_summary.py from the .ncu-rep of scripts/ncu_targets.py: full layer
     shapes, B = 32, dram__bytes_read.sum + dram__bytes_write.sum); (None, None) when the file is absent."""
     try:
-        t = json.load(open(os.path.join(ROOT, 'profiles', 'r3_ncu_traffic.json')))['kernels']
+        t = json.load(open(os.path.join(ROOT, 'profiles', 'r4_ncu_traffic.json')))['kernels']
         return t.get(TOP_KERNEL, {}).get('dram_bytes'), {k: v['dram_bytes'] for k, v in t.items()}
     except Exception:
         return None, None
@@ -315,7 +315,7 @@ def run_b200(args):
                     mma_per_product=3,
                     note='fp32 operands are split into two 16-bit planes (fp32-class results, DESIGN 3.1): every algorithmic '
                          'product costs 3 tensor-core MMAs, so the tensor pipe does 3x `achieved`; ncu tensor-pipe-active '
-                         'and DRAM bytes per launch: profiles/r3_ncu_full.txt')
+                         'and DRAM bytes per launch: profiles/r4_ncu_full.txt')
 
     # ---- end-to-end: host batch in pinned memory -> H2D each step, losses read back each step
     host = [torch.empty(B, 3, size, size, pin_memory=True).uniform_(-1, 1) for _ in range(2)]
