@@ -11,6 +11,7 @@
 // profiles/r2a_umma_shift.txt).  MMA scheme, weight tiles, accumulators and epilogue are those of conv_halo.cu:
 //   per (tap, k16): [hi*hi | hi*lo] += A_hi x [B_hi ; B_lo] (N = 2 BN),  upper half += A_lo x B_hi;  result = lower + upper.
 // Warp roles: 0 patch TMA, 1 MMA (+TMEM alloc), 2..9 epilogue, 10 weight TMA.
+#include <stdlib.h>
 #include <cuda_bf16.h>
 #include "tc_common.cuh"
 #include "conv.h"
@@ -51,6 +52,7 @@ struct Params {
     float alpha, gain;
     int accumulate;          // y += result (the skip branch's data gradient lands on top of the main branch's)
     int bstages;             // weight stages in use (<= Cfg::BSTAGES)
+    int two_term;            // experiment (SG2_GRAD_TERMS=2): drop the A_lo x B_hi product (the input is then effectively bf16)
     int tma_store;           // dense NHWC output: the epilogue stages the tile in shared memory and stores it with TMA (below)
     int stg_off;             // staging tile, bytes after the first weight stage
     int tx_shift, ty_shift;  // log2(tiles_x), log2(tiles_y) when both are powers of two, else -1
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_halo_pl_kernel(const __grid_
                             if (kq >= kqn) break;
                             const uint32_t db = b0_ + kq * 2;
                             mma_f16_words(d, pl0 + arow + kq * 2, a_hi, db, b_hi, idesc2, !(kb == 0 && t == 0 && kq == 0));   // [hi*hi | hi*lo] += A_hi * [B_hi ; B_lo]
-                            mma_f16_words(d + BN, pl1 + arow + kq * 2, a_hi, db, b_hi, idesc, 1);                            //          upper  += A_lo * B_hi
+                            if (!p.two_term) mma_f16_words(d + BN, pl1 + arow + kq * 2, a_hi, db, b_hi, idesc, 1);          //          upper  += A_lo * B_hi
                         }
                         mma_commit(b_empty(s));
                         if (++s == nstages) { s = 0; sph ^= 1; }
@@ -341,6 +343,9 @@ int conv_fwd_halo_pl(const void* x_planes, const ConvParams& p, int accumulate, 
     tp.n_tiles = p.co / bn;
     tp.nkb = (p.ci + 63) / 64;
     tp.act = p.act; tp.alpha = p.alpha; tp.gain = p.gain; tp.accumulate = accumulate;
+    static int terms = 0;
+    if (!terms) { const char* e = getenv("SG2_GRAD_TERMS"); terms = e ? atoi(e) : 3; }
+    tp.two_term = terms == 2;
     auto log2_exact = [](int v) { int l = 0; while ((1 << l) < v) ++l; return (1 << l) == v ? l : -1; };
     tp.tx_shift = log2_exact(tp.tiles_x); tp.ty_shift = log2_exact(tp.tiles_y);
     if (tp.tx_shift < 0 || tp.ty_shift < 0) tp.tx_shift = tp.ty_shift = -1;

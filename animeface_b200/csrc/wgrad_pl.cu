@@ -20,6 +20,7 @@
 //        tile carries the lo plane, so TWO MMAs (x hi, x lo) give all four products; dW = lower + upper half.
 //   Accumulation in TMEM over the CTA's pixel range; every CTA writes its fp32 partial tile to a workspace and a second kernel
 //   adds the splits in a fixed order -> run-to-run identical gradients (round 1 used fp32 atomics).
+#include <stdlib.h>
 #include <cuda_bf16.h>
 #include "tc_common.cuh"
 #include "conv.h"
@@ -41,6 +42,7 @@ struct Params {
     int chunks_per_split;
     int ncols;                // 64 * k
     int stages, stage_bytes, a_bytes;
+    int two_term;             // experiment (SG2_GRAD_TERMS=2): drop the gy_lo x x_hi product (co % 128 == 0 path only)
 };
 
 template <int KW>
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_pl_kernel(const __grid
                     } else {
                         const uint64_t dah = mnmajor_desc(a0 + ko, ABLK, 1024), dal = mnmajor_desc(a0 + 2 * ABLK + ko, ABLK, 1024);
                         mma_bf16(tmem_d, dah, dbh, idesc, (i | kq) != 0);
-                        mma_bf16(tmem_d, dal, dbh, idesc, 1);
+                        if (!p.two_term) mma_bf16(tmem_d, dal, dbh, idesc, 1);
                         mma_bf16(tmem_d, dah, dbl, idesc, 1);
                     }
                 }
@@ -218,6 +220,9 @@ static Plan make_plan(int n, int h, int w, int ci, int co, int k) {
     p.chunks_x = (w + p.cw - 1) / p.cw; p.chunks_y = (h + p.ch - 1) / p.ch;
     p.total_chunks = p.chunks_x * p.chunks_y * ((n + p.cb - 1) / p.cb);
     p.stack = (co % 128 != 0) ? 1 : 0;
+    static int terms = 0;
+    if (!terms) { const char* e = getenv("SG2_GRAD_TERMS"); terms = e ? atoi(e) : 3; }
+    p.two_term = terms == 2;
     p.co_tiles = (co + (p.stack ? 63 : 127)) / (p.stack ? 64 : 128);
     p.ci_tiles = (ci + 63) / 64;
     p.ncols = 64 * k;
