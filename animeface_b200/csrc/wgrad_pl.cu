@@ -42,7 +42,7 @@ struct Params {
     int chunks_per_split;
     int ncols;                // 64 * k
     int stages, stage_bytes, a_bytes;
-    int two_term;             // experiment (SG2_GRAD_TERMS=2): drop the gy_lo x x_hi product (co % 128 == 0 path only)
+    int two_term;             // experiment (SG2_GRAD_TERMS=2 / SG2_WGRAD_TERMS=2): x taken as its bf16 hi plane only (the x_lo products dropped)
 };
 
 template <int KW>
@@ -128,12 +128,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_pl_kernel(const __grid
                     if (p.stack) {
                         const uint64_t da = mnmajor_desc(a0 + ko, ABLK, 1024);             // rows [hi(64) ; lo(64)]
                         mma_bf16(tmem_d, da, dbh, idesc, (i | kq) != 0);
-                        mma_bf16(tmem_d, da, dbl, idesc, 1);
+                        if (!p.two_term) mma_bf16(tmem_d, da, dbl, idesc, 1);
                     } else {
                         const uint64_t dah = mnmajor_desc(a0 + ko, ABLK, 1024), dal = mnmajor_desc(a0 + 2 * ABLK + ko, ABLK, 1024);
                         mma_bf16(tmem_d, dah, dbh, idesc, (i | kq) != 0);
-                        if (!p.two_term) mma_bf16(tmem_d, dal, dbh, idesc, 1);
-                        mma_bf16(tmem_d, dah, dbl, idesc, 1);
+                        mma_bf16(tmem_d, dal, dbh, idesc, 1);
+                        if (!p.two_term) mma_bf16(tmem_d, dah, dbl, idesc, 1);
                     }
                 }
                 mma_commit(empty(s));
@@ -221,7 +221,11 @@ static Plan make_plan(int n, int h, int w, int ci, int co, int k) {
     p.total_chunks = p.chunks_x * p.chunks_y * ((n + p.cb - 1) / p.cb);
     p.stack = (co % 128 != 0) ? 1 : 0;
     static int terms = 0;
-    if (!terms) { const char* e = getenv("SG2_GRAD_TERMS"); terms = e ? atoi(e) : 3; }
+    if (!terms) {
+        const char* e = getenv("SG2_WGRAD_TERMS");
+        if (!e) e = getenv("SG2_GRAD_TERMS");
+        terms = e ? atoi(e) : 3;
+    }
     p.two_term = terms == 2;
     p.co_tiles = (co + (p.stack ? 63 : 127)) / (p.stack ? 64 : 128);
     p.ci_tiles = (ci + 63) / 64;
