@@ -392,10 +392,135 @@ static int launch_ring(const UpfirdnParams& p, cudaStream_t st) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// NCHW filter form (up = down = 1) with coalesced 128-bit row loads and warp shuffles: the ring kernel's thread fetches the 7-wide
+// window of its 4 outputs with 7 scalar loads that overlap 7-fold between neighbours (L1-bound: 0.57 of HBM peak on U4; this
+// kernel: 0.61).  Here a
+// lane loads ONE aligned float4 of the input row (a warp reads 512 contiguous bytes) and takes the 3 values it lacks from the
+// next lane with shuffles; lane 31 only feeds lane 30, so consecutive warps overlap by one group (31 / 32 of the lanes produce
+// outputs).  Output columns of a thread: jx = 4 g + padx0 + e (e < 4), whose windows start inside its own group g.
+// One warp = one work item (plane, strip of STRIP output rows, chunk of 31 groups); rows walk output-stationary like the ring.
+template <int FH, int FW, int STRIP>
+__global__ void __launch_bounds__(256) upfirdn2d_nchw_shfl_kernel(UpfirdnParams p, int gmin, int chunks, int strips) {
+    static_assert(FW <= 4, "a window spans the thread's own group and the next one");
+    float wt[FH][FW];
+#pragma unroll
+    for (int a = 0; a < FH; ++a)
+#pragma unroll
+        for (int b = 0; b < FW; ++b)
+            wt[a][b] = __ldg(p.f + (p.flip ? a : FH - 1 - a) * FW + (p.flip ? b : FW - 1 - b)) * p.gain;
+    bool sep = wt[0][0] != 0.f && p.sepok;
+#pragma unroll
+    for (int a = 0; a < FH; ++a)
+#pragma unroll
+        for (int b = 0; b < FW; ++b) {
+            const float lhs = wt[a][b] * wt[0][0], rhs = wt[a][0] * wt[0][b];
+            sep = sep && fabsf(lhs - rhs) <= 2.4e-7f * fabsf(rhs);
+        }
+    float fx[FW], fy[FH];
+#pragma unroll
+    for (int b = 0; b < FW; ++b) fx[b] = sep ? wt[0][b] / wt[0][0] : 0.f;
+#pragma unroll
+    for (int a = 0; a < FH; ++a) fy[a] = wt[a][0];
+
+    const int lane = threadIdx.x & 31;
+    const long long item = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const long long nitems = (long long)p.n * p.c * strips * chunks;
+    if (item >= nitems) return;
+    const int chunk = (int)(item % chunks);
+    const int strip = (int)((item / chunks) % strips);
+    const long long plane = item / ((long long)chunks * strips);
+    const int g = gmin + chunk * 31 + lane;                 // aligned input group of this lane: columns 4g .. 4g+3
+    const bool gok = g >= 0 && 4 * g < p.in_w;              // in_w % 4 == 0: a group is inside the row or outside, never astride
+    const int jx0 = 4 * g + p.padx0;                        // first output column of this lane
+    const int jy0 = strip * STRIP, iy0 = jy0 - p.pady0;
+    const float* xp = (const float*)p.x + plane * p.in_h * p.in_w + 4 * g;
+    float* yp = (float*)p.y + plane * p.out_h * p.out_w;
+    constexpr int NROWS = STRIP - 1 + FH;
+    float acc[FH][4];
+#pragma unroll
+    for (int i = 0; i < FH; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
+    auto walk = [&](auto separable) {
+        constexpr bool SEP = decltype(separable)::value;
+#pragma unroll
+        for (int k = 0; k < NROWS; ++k) {
+            const int iy = iy0 + k;
+            float4 v = f4zero();
+            if (gok && (unsigned)iy < (unsigned)p.in_h) v = ldg4(xp + (size_t)iy * p.in_w);
+            float w[7];
+            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+            w[4] = __shfl_down_sync(0xffffffffu, v.x, 1); w[5] = __shfl_down_sync(0xffffffffu, v.y, 1); w[6] = __shfl_down_sync(0xffffffffu, v.z, 1);
+            float h[4];
+            if (SEP) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    h[e] = 0.f;
+#pragma unroll
+                    for (int b = 0; b < FW; ++b) h[e] = fmaf(fx[b], w[e + b], h[e]);
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < FH; ++a) {
+                if (k - a >= 0 && k - a < STRIP) {
+                    const int s = k - a;                        // input row k is tap row a of output row s
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (SEP) acc[s % FH][e] = fmaf(fy[a], h[e], acc[s % FH][e]);
+                        else {
+#pragma unroll
+                            for (int b = 0; b < FW; ++b) acc[s % FH][e] = fmaf(wt[a][b], w[e + b], acc[s % FH][e]);
+                        }
+                    }
+                    if (a == FH - 1) {                          // last tap row of output row s: store, recycle the accumulator
+                        if (lane < 31 && jy0 + s < p.out_h) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if ((unsigned)(jx0 + e) < (unsigned)p.out_w) __stcs(yp + (size_t)(jy0 + s) * p.out_w + jx0 + e, acc[s % FH][e]);
+                        }
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[s % FH][e] = 0.f;
+                    }
+                }
+            }
+        }
+    };
+    if (sep) walk(BoolTag<true>{}); else walk(BoolTag<false>{});
+}
+
+template <int FH, int FW>
+static int launch_nchw_shfl(const UpfirdnParams& p_in, cudaStream_t st) {
+    UpfirdnParams p = p_in;
+    static int sepok = -1;
+    if (sepok < 0) { const char* e = getenv("SG2_UPF_SEP"); sepok = e ? atoi(e) != 0 : 1; }
+    p.sepok = sepok;
+    constexpr int STRIP = 32;
+    // groups whose windows reach an output column: jx = 4g + padx0 + e in [0, out_w)  ->  g in [gmin, gmax]
+    auto fdiv = [](int a, int b) { int q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; };
+    const int gmin = -fdiv(p.padx0 + 3, 4), gmax = fdiv(p.out_w - 1 - p.padx0, 4);
+    const int chunks = (int)ceil_div(gmax - gmin + 1, 31), strips = (int)ceil_div(p.out_h, STRIP);
+    const long long items = (long long)p.n * p.c * strips * chunks;
+    upfirdn2d_nchw_shfl_kernel<FH, FW, STRIP><<<(unsigned)ceil_div(items, 8), 256, 0, st>>>(p, gmin, chunks, strips);
+    return launched("upfirdn2d_nchw_shfl");
+}
+
 // returns SG2_ENOTSUP when the call is not one of the ring shapes
 template <class V>
 static int try_ring(const UpfirdnParams& p, cudaStream_t st) {
     if (p.upx != 1 || p.upy != 1 || p.downx != p.downy || p.fh != p.fw) return SG2_ENOTSUP;
+    if constexpr (sizeof(V) == 4) {
+        // NCHW filter form with 16-byte aligned rows: the shuffle kernel (SG2_UPF_NCHW_SHFL=0 keeps the ring, for the A/B)
+        static int shfl = -1;
+        if (shfl < 0) { const char* e = getenv("SG2_UPF_NCHW_SHFL"); shfl = e ? atoi(e) != 0 : 1; }
+        // ... when its lanes are reasonably full: a row of G groups takes ceil(G / 31) warps (U4: 65 groups -> 3 warps, 70 % of the lanes)
+        const int groups = (p.out_w - 1 - p.padx0) / 4 + (p.padx0 + 3) / 4 + 1;
+        const bool full = groups * 100 >= 65 * 31 * (int)ceil_div(groups, 31);
+        if (shfl && full && p.downx == 1 && (p.in_w % 4) == 0 && (((uintptr_t)p.x) & 15) == 0 && p.padx0 >= 0) {
+            if (p.fh == 4) return launch_nchw_shfl<4, 4>(p, st);
+            if (p.fh == 3) return launch_nchw_shfl<3, 3>(p, st);
+        }
+    }
     if (p.fh == 4 && p.downx == 1) return launch_ring<V, 4, 4, 1>(p, st);
     if (p.fh == 4 && p.downx == 2) return launch_ring<V, 4, 4, 2>(p, st);
     if (p.fh == 3 && p.downx == 1) return launch_ring<V, 3, 3, 1>(p, st);
