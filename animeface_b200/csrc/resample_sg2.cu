@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(256) up2x_adj_strip_kernel(const float* __rest
         for (int b = 0; b < 6; ++b) v[b] = ldg4(row + jxo[b]);
         float4 r = scale4(v[0], Ax[0] * keep);
 #pragma unroll
-        for (int b = 1; b < 6; ++b) fma4(r, Ax[b] * keep, v[b]);
+        for (int b = 1; b < 6; ++b) fma4_x2(r, Ax[b] * keep, v[b]);
         return r;
     };
     float4 H[6];
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(256) up2x_adj_strip_kernel(const float* __rest
         axis_w_adj(iy, h, blur, Ay);
         float4 acc = f4zero();
 #pragma unroll
-        for (int a = 0; a < 6; ++a) fma4(acc, Ay[a], H[a]);
+        for (int a = 0; a < 6; ++a) fma4_x2(acc, Ay[a], H[a]);
         st4_cs(go + ((size_t)iy * w + ix) * c, mul4(acc, sc));
     }
 }

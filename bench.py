@@ -163,7 +163,7 @@ def upfirdn2d_rates(dev, peaks):
     write of y), CUDA events, L2 flushed between iterations, median of 7."""
     import torch
     from animeface_b200.ops import upfirdn2d as U
-    from animeface_b200.ops.resample import avgpool2, upsample2x_blur
+    from animeface_b200.ops.resample import Up2xAdjFn, avgpool2, upsample2x_blur
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def rate(fn, nbytes):
@@ -186,6 +186,7 @@ def upfirdn2d_rates(dev, peaks):
         x = cl(32, 64, 128, 128)
         out['U1 up2 bilinear+blur [32,64,128,128]->256^2 (fused, SG2 generator)'] = rate(lambda: upsample2x_blur(x), x.numel() * 4 * 5)
         g = cl(32, 64, 256, 256)
+        out['U1 adjoint (backward of the fused up2 + blur) [32,64,256,256]->128^2'] = rate(lambda: Up2xAdjFn.apply(g, True), g.numel() * 4 * 1.25)
         out['U3 down2 [1,1] = AvgPool2 [32,64,256,256] (SG2 discriminator)'] = rate(lambda: avgpool2(g), g.numel() * 4 * 1.25)
         f = U.setup_filter([1, 3, 3, 1], device=dev)
         out['U4 filter 4x4 pad 2 -> 257^2, NHWC (SG3-style discriminator)'] = rate(lambda: U.upfirdn2d(g, f, padding=2), (g.numel() + 32 * 64 * 257 * 257) * 4)
