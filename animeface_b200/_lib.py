@@ -55,6 +55,8 @@ SIGNATURES = {
     'sg2_conv2d_fwd_planes': (_int, [_vp, _vp, _vp, _i64p, _int, _int, _int, _int, _int, _int, _vp, _vp, _int, _f, _f, _int, _vp]),
     'sg2_conv2d_wgrad_planes_workspace': (_i64, [_int, _int, _int, _int, _int, _int]),
     'sg2_conv2d_wgrad_planes': (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _f, _int, _vp]),
+    'sg2_thin_in_bwd_workspace': (_i64, [_int, _int, _int, _int]),
+    'sg2_thin_in_bwd': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _f, _f, _f, _vp]),
     'sg2_demod_fwd': (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _int, _f, _f, _vp]),
     'sg2_demod_bwd': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _f, _vp]),
     'sg2_filtered_lrelu': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int] + [_int] * 16 + [_f, _f, _f, _f, _int, _vp]),

@@ -355,6 +355,22 @@ class ConvBiasActFn(torch.autograd.Function):
         x, w, y = ctx.saved_tensors
         co = w.shape[0]
         gb = None
+        n_, ci_, h_, wd_ = x.shape
+        if (not torch.is_grad_enabled() and ci_ <= 4 and w.shape[2] == 1 and ctx.slope is not None and co in (4, 8, 16, 32, 64)
+                and gy.dtype == torch.float32):
+            # thin input (from_rgb): leaky-ReLU gradient, bias / weight gradient and (when asked for) the image gradient in ONE pass
+            # over (gy, y) -- csrc/thin_bwd.cu
+            lib = _lib.load()
+            gyc, yc, xc = _cl(gy), _cl(y), _cl(x)
+            need_gx, need_gw, need_gb = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+            gx = torch.empty_like(xc) if need_gx else None
+            gw = torch.empty_like(w) if need_gw else None
+            gb = torch.empty((co,), dtype=torch.float32, device=gy.device) if need_gb else None
+            ws = _workspace(lib.sg2_thin_in_bwd_workspace(n_, h_ * wd_, ci_, co), gy.device, 'sg2_thin_in_bwd_workspace')
+            _lib.check(lib.sg2_thin_in_bwd(gyc.data_ptr(), yc.data_ptr(), xc.data_ptr(), w.detach().contiguous().data_ptr(), _lib.ptr(gx),
+                                           _lib.ptr(gw), _lib.ptr(gb), ws.data_ptr(), n_, h_ * wd_, ci_, co, float(ctx.slope), float(ctx.gain),
+                                           float(ctx.coef), _lib.stream_ptr(gy)), 'sg2_thin_in_bwd')
+            return gx, gw, gb, None, None, None
         if ctx.gain != 1.0:
             gy = gy * ctx.gain               # y = gain * lrelu(t), gain > 0: sign(y) = sign(t), d y / d t = gain * lrelu'(y)
         if torch.is_grad_enabled() or co % 4 != 0:

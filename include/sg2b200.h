@@ -235,6 +235,16 @@ int sg2_conv2d_wgrad_planes(const void* x_planes, const void* gy_planes, float* 
                             int n, int h, int w, int ci, int co, int k, float coef, int accumulate,
                             sg2_stream_t stream);
 
+/* backward of a thin-input 1x1 convolution + bias + leaky ReLU ---------------- *
+ * replaces: convolution_backward + LeakyReLU backward + the bias reduction behind Discriminator.from_rgb
+ *           (implementations/StyleGAN2/model.py:383-384: Conv2d('elr', 3, 32, 1) + LeakyReLU) in ONE pass over (gy, y):
+ *             gu = gy * gain * (y > 0 ? 1 : slope);  gw[o][c] = coef * sum gu x;  gb[o] = sum gu;  gx[pix][c] = coef * sum_o gu w[o][c]
+ * gy, y [n,hw,co] NHWC dense (co in {4,8,16,32,64}); x [n,hw,cin] (cin <= 4); w [co][cin] (the reference layout, k = 1).
+ * gx, gw, gb may be NULL.  workspace: sg2_thin_in_bwd_workspace bytes.  Deterministic (block partials added in order).         */
+int64_t sg2_thin_in_bwd_workspace(int n, int hw, int cin, int co);
+int sg2_thin_in_bwd(const float* gy, const float* y, const float* x, const float* w, float* gx, float* gw, float* gb,
+                    void* workspace, int n, int hw, int cin, int co, float slope, float gain, float coef, sg2_stream_t stream);
+
 /* demodulation coefficient ----------------------------------------------------- *
  * replaces: the tensor expression of implementations/StyleGAN2/model.py:115-120 reduced to the [B,Co] coefficient
  *           d[b,o] = rsqrt(coef^2 * sum_i s[b,i]^2 * sum_k w[o,i,k]^2 + eps)   (pow, reduce, sgemm, mul, add, rsqrt)
