@@ -24,27 +24,54 @@ __device__ __forceinline__ void block_reduce_store(float4 acc, float (*sh)[68], 
     __syncthreads();
 }
 
-// out[b,c] += sum_{i in slice} a*bm ; optionally a_out = a * scale[b,c]
+// chunk of channels a block covers: 64, or 32 for 32-channel tensors so that no thread idles (planes.cu uses the same layout)
+__host__ __device__ __forceinline__ int aux_chunk_width(int c) { return (c % 64 == 0 || c > 32) ? 64 : 32; }
+
+__device__ __forceinline__ void block_reduce_store_cw(float4 acc, float* sh, float* out_row, int c, int cbase, int cw, bool part) {
+    const int tpp = cw >> 2, rows = 256 / tpp, pitch = cw + 4;
+    const int q = threadIdx.x % tpp, pl = threadIdx.x / tpp;
+    float* mine = sh + pl * pitch + q * 4;
+    mine[0] = acc.x; mine[1] = acc.y; mine[2] = acc.z; mine[3] = acc.w;
+    __syncthreads();
+    if ((int)threadIdx.x < cw) {
+        float s = 0.f;
+        for (int i = 0; i < rows; ++i) s += sh[i * pitch + threadIdx.x];
+        const int cc = cbase + threadIdx.x;
+        if (cc < c) { if (part) out_row[cc] = s; else atomicAdd(out_row + cc, s); }
+    }
+    __syncthreads();
+}
+
+// out[b,c] += sum_{i in slice} a*bm ; optionally a_out = a * scale[b,c].  Two pixels per iteration: their loads are in flight together.
 __global__ void __launch_bounds__(256) scale_reduce_hw_kernel(const float* __restrict__ a, const float* __restrict__ bm,
                                                               const float* __restrict__ scale, float* __restrict__ a_out,
                                                               float* __restrict__ out, float* __restrict__ part, int n, int hw, int c, int slice) {
-    __shared__ float sh[16][68];
-    const int q = threadIdx.x & 15, pl = threadIdx.x >> 4;
-    const int c0 = blockIdx.x * 64 + q * 4, b = blockIdx.y;
+    __shared__ float sh[32 * 36];                          // rows x (cw + 4): 16 x 68 or 32 x 36
+    const int cw = aux_chunk_width(c), tpp = cw >> 2, rows = 256 / tpp;
+    const int q = threadIdx.x % tpp, pl = threadIdx.x / tpp;
+    const int c0 = blockIdx.x * cw + q * 4, b = blockIdx.y;
     const int beg = blockIdx.z * slice, end = min(hw, beg + slice);
     float4 acc = f4zero();
     if (c0 < c) {
         const long long base = (long long)b * hw * c + c0;
         float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
         if (a_out && scale) sc = ldg4(scale + (long long)b * c + c0);
-        for (int i = beg + pl; i < end; i += 16) {
-            const float4 v = ldg4(a + base + (long long)i * c);
-            if (a_out) st4_cs(a_out + base + (long long)i * c, mul4(v, sc));
-            acc = add4(acc, bm ? mul4(v, ldg4(bm + base + (long long)i * c)) : v);
+        auto one = [&](long long o, const float4& v, const float4& m) {
+            if (a_out) st4_cs(a_out + o, mul4(v, sc));
+            acc = add4(acc, bm ? mul4(v, m) : v);
+        };
+        int i = beg + pl;
+        const long long step = (long long)rows * c;
+        for (; i + rows < end; i += 2 * rows) {
+            const long long o = base + (long long)i * c;
+            const float4 v0 = ldg4(a + o), v1 = ldg4(a + o + step);
+            const float4 m0 = bm ? ldg4(bm + o) : f4zero(), m1 = bm ? ldg4(bm + o + step) : f4zero();
+            one(o, v0, m0); one(o + step, v1, m1);
         }
+        if (i < end) { const long long o = base + (long long)i * c; one(o, ldg4(a + o), bm ? ldg4(bm + o) : f4zero()); }
     }
-    if (part) block_reduce_store(acc, sh, part + ((long long)blockIdx.z * n + b) * c, c, blockIdx.x * 64, true);
-    else block_reduce_store(acc, sh, out + (long long)b * c, c, blockIdx.x * 64);
+    if (part) block_reduce_store_cw(acc, sh, part + ((long long)blockIdx.z * n + b) * c, c, blockIdx.x * cw, cw, true);
+    else block_reduce_store_cw(acc, sh, out + (long long)b * c, c, blockIdx.x * cw, cw, false);
 }
 
 // One pass over (gy, y):  gu = gy * act'(y);  g_acc = gu * d;  gb_part[b,o] += sum gu;
@@ -100,8 +127,9 @@ __global__ void __launch_bounds__(256) aux_sum_slices_kernel(const float* __rest
     out[i] = s;
 }
 
-static void pick_grid(int n, int hw, int c, dim3& grid, int& slice) {
-    const int cchunks = (c + 63) / 64;
+static void pick_grid(int n, int hw, int c, dim3& grid, int& slice, bool narrow = false) {
+    const int cw = narrow ? aux_chunk_width(c) : 64;
+    const int cchunks = (c + cw - 1) / cw;
     long long want = std::max<long long>(1, (4LL * num_sms()) / ((long long)cchunks * n));
     int slices = (int)std::min<long long>(want, ceil_div(hw, 64));
     slice = (int)ceil_div(hw, slices);
@@ -132,7 +160,7 @@ extern "C" int sg2_scale_reduce_hw(const float* a, const float* bm, const float*
     cudaStream_t st = (cudaStream_t)stream;
     if (!workspace) SG2_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n * c, st));
     dim3 grid; int slice;
-    pick_grid(n, hw, c, grid, slice);
+    pick_grid(n, hw, c, grid, slice, true);
     scale_reduce_hw_kernel<<<grid, 256, 0, st>>>(a, bm, scale, a_out, out, (float*)workspace, n, hw, c, slice);
     int rc = launched("scale_reduce_hw");
     if (rc || !workspace) return rc;
