@@ -193,21 +193,23 @@ __global__ void __launch_bounds__(128) linear_bwd_data_kernel(const float* __res
     }
 }
 
-// grid (k slices of 128, feature groups of 4): warp = feature n, lane = 4 consecutive k
+// grid (k slices of 128, feature groups of 4 * FPW): a warp owns FPW features, a lane 4 consecutive k.  FPW = 4 for the wide layer
+// (K = 8192: every x row slice is then fetched by N / 16 blocks instead of N / 4), 1 for the 512-wide layers (more blocks).
+template <int FPW>
 __global__ void __launch_bounds__(128) linear_bwd_weight_kernel(const float* __restrict__ gy, const float* __restrict__ y, const float* __restrict__ x,
                                                                 float* __restrict__ gw, float* __restrict__ gb, int B, int K, int N,
                                                                 float coef, float gain, float slope) {
     const int lane = threadIdx.x & 31;
-    const int n = blockIdx.y * 4 + (threadIdx.x >> 5);
-    if (n >= N) return;
+    const int n0 = (blockIdx.y * 4 + (threadIdx.x >> 5)) * FPW;
+    if (n0 >= N) return;
     const int k0 = blockIdx.x * 128 + lane * 4;
     const bool vec = (K & 3) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)gw & 15) == 0;
-    float4 acc = f4zero();
-    float sb = 0.f;
+    float4 acc[FPW];
+    float sb[FPW];
+#pragma unroll
+    for (int f = 0; f < FPW; ++f) { acc[f] = f4zero(); sb[f] = 0.f; }
 #pragma unroll 8
     for (int b = 0; b < B; ++b) {                     // unrolled: 8 rows of loads in flight (the loop is pure load latency otherwise)
-        const float g = gu_of(gy, y, (long long)b * N + n, gain, slope);
-        sb += g;
         const float* xr = x + (long long)b * K;
         float4 xv = f4zero();
         if (vec) { if (k0 < K) xv = ldg4(xr + k0); }
@@ -215,17 +217,27 @@ __global__ void __launch_bounds__(128) linear_bwd_weight_kernel(const float* __r
             xv.x = k0 < K ? __ldg(xr + k0) : 0.f; xv.y = k0 + 1 < K ? __ldg(xr + k0 + 1) : 0.f;
             xv.z = k0 + 2 < K ? __ldg(xr + k0 + 2) : 0.f; xv.w = k0 + 3 < K ? __ldg(xr + k0 + 3) : 0.f;
         }
-        fma4(acc, g, xv);
+#pragma unroll
+        for (int f = 0; f < FPW; ++f) {
+            const float g = n0 + f < N ? gu_of(gy, y, (long long)b * N + n0 + f, gain, slope) : 0.f;
+            sb[f] += g;
+            fma4(acc[f], g, xv);
+        }
     }
-    float* dst = gw + (long long)n * K + k0;
-    if (vec) { if (k0 < K) st4(dst, scale4(acc, coef)); }
-    else {
-        if (k0 < K) dst[0] = acc.x * coef;
-        if (k0 + 1 < K) dst[1] = acc.y * coef;
-        if (k0 + 2 < K) dst[2] = acc.z * coef;
-        if (k0 + 3 < K) dst[3] = acc.w * coef;
+#pragma unroll
+    for (int f = 0; f < FPW; ++f) {
+        const int n = n0 + f;
+        if (n >= N) break;
+        float* dst = gw + (long long)n * K + k0;
+        if (vec) { if (k0 < K) st4(dst, scale4(acc[f], coef)); }
+        else {
+            if (k0 < K) dst[0] = acc[f].x * coef;
+            if (k0 + 1 < K) dst[1] = acc[f].y * coef;
+            if (k0 + 2 < K) dst[2] = acc[f].z * coef;
+            if (k0 + 3 < K) dst[3] = acc[f].w * coef;
+        }
+        if (gb && blockIdx.x == 0 && lane == 0) gb[n] = sb[f];
     }
-    if (gb && blockIdx.x == 0 && lane == 0) gb[n] = sb;
 }
 
 // y = x / (sqrt(mean_k x^2) + eps): one warp per row
@@ -292,9 +304,14 @@ extern "C" int sg2_linear_bwd_weight(const float* gy, const float* y, const floa
                                      float coef, float gain, float slope, sg2_stream_t stream) {
     SG2_REQUIRE(gy && x && gw, "linear_bwd_weight: null pointer");
     SG2_REQUIRE(B > 0 && K > 0 && N > 0, "linear_bwd_weight: empty tensor");
-    dim3 grid((unsigned)ceil_div(K, 128), (unsigned)ceil_div(N, 4));
-    SG2_REQUIRE(grid.y <= 65535, "linear_bwd_weight: too many output features (%d)", N);
-    lin::linear_bwd_weight_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(gy, y, x, gw, gb, B, K, N, coef, gain, slope);
+    if (ceil_div(K, 128) * ceil_div(N, 16) >= 2 * num_sms()) {
+        dim3 grid((unsigned)ceil_div(K, 128), (unsigned)ceil_div(N, 16));
+        lin::linear_bwd_weight_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>(gy, y, x, gw, gb, B, K, N, coef, gain, slope);
+    } else {
+        dim3 grid((unsigned)ceil_div(K, 128), (unsigned)ceil_div(N, 4));
+        SG2_REQUIRE(grid.y <= 65535, "linear_bwd_weight: too many output features (%d)", N);
+        lin::linear_bwd_weight_kernel<1><<<grid, 128, 0, (cudaStream_t)stream>>>(gy, y, x, gw, gb, B, K, N, coef, gain, slope);
+    }
     return launched("linear_bwd_weight");
 }
 
