@@ -175,8 +175,11 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
     const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const int kk2 = k * k;
     if (idx >= (long long)co * ci * kk2) return;
-    const int tap = (int)(idx % kk2);
-    const int c_i = (int)((idx / kk2) % ci), c_o = (int)(idx / ((long long)kk2 * ci));
+    // thread order (c_o, tap, c_i): consecutive threads read consecutive workspace columns (coalesced, `splits` times) and make one
+    // scattered write each; the dw order (tap fastest) read 4 bytes out of every 256
+    const int c_i = (int)(idx % ci);
+    const int tap = (int)((idx / ci) % kk2), c_o = (int)(idx / ((long long)kk2 * ci));
+    const long long oidx = ((long long)c_o * ci + c_i) * kk2 + tap;
     const int dyi = tap / k, dxi = tap % k;
     const int mt = stack ? 64 : 128;
     const int tile = (dyi * ci_tiles + c_i / 64) * co_tiles + c_o / mt;
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
         s += v;
     }
     s *= coef;
-    dw[idx] = accumulate ? dw[idx] + s : s;
+    dw[oidx] = accumulate ? dw[oidx] + s : s;
 }
 
 struct Plan { Params p; int tiles, splits, smem; bool ok; };
