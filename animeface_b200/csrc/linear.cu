@@ -137,14 +137,14 @@ __device__ __forceinline__ float gu_of(const float* gy, const float* y, long lon
     return (y && !(__ldg(y + i) > 0.f)) ? g * slope : g;
 }
 
-// grid (k slices of 32 * KV, row groups of 8); 4 warps split n, reduced through shared memory.  KV = 4 (128-bit weight loads)
+// grid (k slices of 32 * KV, row groups of 8); NW warps split n, reduced through shared memory in warp order.  KV = 4 (128-bit weight loads)
 // when K is large enough to fill the machine that way, KV = 1 (more, narrower CTAs) for the 512-wide mapping / affine layers.
-template <int KV>
-__global__ void __launch_bounds__(128) linear_bwd_data_kernel(const float* __restrict__ gy, const float* __restrict__ y, const float* __restrict__ w,
+template <int KV, int NW>
+__global__ void __launch_bounds__(NW * 32) linear_bwd_data_kernel(const float* __restrict__ gy, const float* __restrict__ y, const float* __restrict__ w,
                                                               float* __restrict__ gx, int B, int K, int N, float coef, float gain, float slope) {
     constexpr int R = 8, NC = 512, KS = 32 * KV;
     __shared__ float gu[R][NC];
-    __shared__ float red[4][R][KS];
+    __shared__ float red[NW][R][KS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b0 = blockIdx.y * R, rows = min(R, B - b0);
     const int k0 = blockIdx.x * KS + lane * KV;
@@ -157,13 +157,13 @@ __global__ void __launch_bounds__(128) linear_bwd_data_kernel(const float* __res
     for (int n0 = 0; n0 < N; n0 += NC) {
         const int nn = min(NC, N - n0);
         __syncthreads();
-        for (int i = threadIdx.x; i < R * nn; i += 128) {
+        for (int i = threadIdx.x; i < R * nn; i += NW * 32) {
             const int r = i / nn, c = i % nn;
             gu[r][c] = r < rows ? gu_of(gy, y, (long long)(b0 + r) * N + n0 + c, gain, slope) : 0.f;
         }
         __syncthreads();
 #pragma unroll 8
-        for (int c = warp; c < nn; c += 4) {           // unrolled: 8 weight rows in flight
+        for (int c = warp; c < nn; c += NW) {          // unrolled: 8 weight rows in flight per warp
             const float* wr = w + (long long)(n0 + c) * K;
             float wv[KV];
             if (vec) {
@@ -186,10 +186,13 @@ __global__ void __launch_bounds__(128) linear_bwd_data_kernel(const float* __res
 #pragma unroll
         for (int e = 0; e < KV; ++e) red[warp][r][lane * KV + e] = acc[r][e];
     __syncthreads();
-    for (int i = threadIdx.x; i < R * KS; i += 128) {
+    for (int i = threadIdx.x; i < R * KS; i += NW * 32) {
         const int r = i / KS, kk = i % KS;
         const int k = blockIdx.x * KS + kk;
-        if (r < rows && k < K) gx[(long long)(b0 + r) * K + k] = coef * (red[0][r][kk] + red[1][r][kk] + red[2][r][kk] + red[3][r][kk]);
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < NW; ++j) t += red[j][r][kk];
+        if (r < rows && k < K) gx[(long long)(b0 + r) * K + k] = coef * t;
     }
 }
 
@@ -292,10 +295,10 @@ extern "C" int sg2_linear_bwd_data(const float* gy, const float* y, const float*
     SG2_REQUIRE(B > 0 && K > 0 && N > 0, "linear_bwd_data: empty tensor");
     if (ceil_div(K, 128) * ceil_div(B, 8) >= num_sms()) {
         dim3 grid((unsigned)ceil_div(K, 128), (unsigned)ceil_div(B, 8));
-        lin::linear_bwd_data_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>(gy, y, w, gx, B, K, N, coef, gain, slope);
+        lin::linear_bwd_data_kernel<4, 4><<<grid, 128, 0, (cudaStream_t)stream>>>(gy, y, w, gx, B, K, N, coef, gain, slope);
     } else {
         dim3 grid((unsigned)ceil_div(K, 32), (unsigned)ceil_div(B, 8));
-        lin::linear_bwd_data_kernel<1><<<grid, 128, 0, (cudaStream_t)stream>>>(gy, y, w, gx, B, K, N, coef, gain, slope);
+        lin::linear_bwd_data_kernel<1, 8><<<grid, 256, 0, (cudaStream_t)stream>>>(gy, y, w, gx, B, K, N, coef, gain, slope);
     }
     return launched("linear_bwd_data");
 }
